@@ -1,0 +1,36 @@
+"""pytest configuration: registers the ``gpu`` marker and puts the package directory on sys.path.
+
+``-m "not gpu"`` runs here (no GPU): oracle vs golden vectors, host logic, C-ABI symbol export.
+``-m gpu`` runs on a B200: parity of libkspec.so (through the ctypes C-ABI) against the oracle.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "prgs-sdr-kspecanal_b200")
+for p in (PKG, ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+    g = {k: z[k] for k in z.files}
+    if "params" in g:
+        g["params"] = json.loads(str(g["params"]))
+    return g
+
+
+@pytest.fixture
+def golden():
+    return load_golden
