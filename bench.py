@@ -1,0 +1,314 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the kspec spectrum hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload): the cfg-1 kernel configuration of BASELINE.json -- zeroSpan, fftSize 2048, hanning window,
+50 % overlap (curScanNonOverlap 0.5), curScanCumuMode AVG, per-scan dB + Max/Min/Avg + one 512-bin MAX waterfall row --
+on a long synthetic capture (tones + noise): 2^28 complex64 IQ samples (16384 scans, 2 GiB) PER GPU per step, so the
+input is far larger than L2 (126 MB) and every step streams from HBM.  A "step" = one pass of the hot path over that
+capture.  N > 1: the capture is N times longer and sharded by scan range (weak scaling); only the per-bin
+Max/Min/Avg vectors are all-reduced (NCCL).
+
+  value   IQ Msamples/s, whole job, inputs resident in HBM (CUDA events on the library's stream, max over ranks)
+  e2e     same metric through the public host-buffer call kspec_zerospan_batch: pinned host IQ -> H2D -> kernels ->
+          D2H of waterfall rows + Max/Min/Avg, all inside the timed region
+  roofline  HBM: algorithmic bytes per launch of the fused scan kernel / its measured duration / measured HBM peak
+  cpu_baseline  the oracle port (numpy float64, the reference's algorithm) on the host cores, bounded sample
+
+--impl reference times the reference algorithm (oracle port; the Python reference itself cannot travel to the GPU
+box) on all host cores for the same metric/config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "prgs-sdr-kspecanal_b200"))
+sys.path.insert(0, ROOT)
+
+F, R_NONOVERLAP, GAIN, XRES, FS = 2048, 0.5, 19.1, 512, 2.4e6
+S = F * 8
+LOG2_SAMPLES = int(os.environ.get("KSPEC_BENCH_LOG2_SAMPLES", "28"))
+N_SCANS = (1 << LOG2_SAMPLES) // S
+BASE_SCANS = min(1024, N_SCANS)          # synthetic block that is tiled to the full capture
+WORKLOAD = ("zeroSpan fftSize 2048 hanning 50%% overlap cumuAVG, complex64 ingest, %d scans x %d samples (2^%d IQ samples, "
+            "%.2f GiB) per GPU per step, dB + Max/Min/Avg + 512-bin MAX waterfall row per scan" % (N_SCANS, S, LOG2_SAMPLES, N_SCANS * S * 8 / 2 ** 30))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region"""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        pw = [float(r[3]) for r in self.rows if len(r) > 3 and r[3].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(self.rows), "reasons": sorted(reasons)}
+
+
+def base_capture():
+    from kspec import synth
+    return synth.tones_noise(BASE_SCANS * S, seed=1)
+
+
+def algorithmic_bytes(n_scans):
+    """every input sample once (complex64, 8 B), one 512-bin float32 waterfall row per scan,
+    Max/Min/Avg vectors and the window table once."""
+    return n_scans * S * 8 + n_scans * XRES * 4 + 3 * F * 4 + F * 4
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU: the reference algorithm (oracle port) on host cores
+# ---------------------------------------------------------------------------------------------------------------
+CPU_BLOCK = 64      # scans synthesised per process; the timed loop walks this block repeatedly
+
+
+def _cpu_worker(args):
+    seed, n_scans = args
+    from kspec import synth
+    from oracle import kspec_oracle as O
+    win = O.window_table("hanning", F)
+    x = synth.tones_noise(CPU_BLOCK * S, seed=seed).astype(np.complex128)    # the reference's dtype (K:335)
+    t0 = time.perf_counter()
+    state = None
+    done = 0
+    while done < n_scans:
+        n = min(CPU_BLOCK, n_scans - done)
+        lin = [O.curscan(x[k * S:(k + 1) * S], F, R_NONOVERLAP, win, "AVG") for k in range(n)]
+        z = O.zerospan(lin, GAIN, XRES, "MAX", state=state)
+        state = (z["max"], z["min"], z["avg"])
+        done += n
+    return time.perf_counter() - t0
+
+
+def cpu_reference(n_procs, scans_per_proc, reps=1):
+    """throughput (IQ Msamples/s) of the reference algorithm with n_procs processes each doing scans_per_proc scans"""
+    import multiprocessing as mp
+    best = None
+    ctx = mp.get_context("fork")
+    for _ in range(reps):
+        if n_procs == 1:
+            wall = _cpu_worker((1, scans_per_proc))          # the worker times its compute loop only
+        else:
+            with ctx.Pool(n_procs) as pool:
+                times = pool.map(_cpu_worker, [(i + 1, scans_per_proc) for i in range(n_procs)])
+            wall = max(times)
+        v = n_procs * scans_per_proc * S / wall / 1e6
+        best = v if best is None else max(best, v)
+    return best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    procs = min(cores, 64)
+    scans = 640                                  # ~0.7 s of CPU work per process per step
+    for _ in range(max(args.warmup, 0)):
+        cpu_reference(procs, 8)
+    t0 = time.perf_counter()
+    vals = [cpu_reference(procs, scans) for _ in range(args.steps)]
+    wall = time.perf_counter() - t0
+    v = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": "IQ Msamples/s via window+FFT+max/min/avg at fftSize 2048", "value": v, "unit": "Msamples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / max(args.steps, 1) * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": "%d processes x %d scans of the same configuration per step" % (procs, scans)},
+        "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": procs, "kind": "port",
+                         "sample": "%d scans (%d IQ samples) per step, numpy float64 oracle port of kspecanal.py:351-397,464-484" % (procs * scans, procs * scans * S)},
+        "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU
+# ---------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from kspec import _ffi
+    from kspec.engine import Plan
+    from oracle import kspec_oracle as O          # cpu_baseline leg + window table only
+
+    win = O.window_table("hanning", F)
+    plan = Plan(F, S, R_NONOVERLAP, win, "AVG", _ffi.IN_C64, precision="f32", device=local)
+    info = plan.info
+    base = base_capture()
+    # device-resident capture: the synthetic block tiled N_SCANS/BASE_SCANS times (content does not affect timing)
+    d_samples = plan.dev_alloc(N_SCANS * S * 8)
+    for i in range(N_SCANS // BASE_SCANS):
+        plan.dev_upload(d_samples, base, offset=i * base.nbytes)
+    # pinned host copy for the end-to-end leg
+    pinned = _ffi.PinnedBuffer(N_SCANS * S * 8)
+    host = pinned.view(np.complex64)
+    for i in range(N_SCANS // BASE_SCANS):
+        host[i * len(base):(i + 1) * len(base)] = base
+
+    comm = None
+    if world > 1:
+        comm = _make_comm(world, rank, local, dist)
+    total_scans = N_SCANS * world
+    base_idx = rank * N_SCANS
+
+    def barrier():
+        plan.sync()
+        if dist is not None:
+            dist.barrier()
+
+    def step_dev():
+        plan.zerospan_batch_dev(d_samples, N_SCANS, GAIN, XRES, "MAX", rows=None, want_hm=True,
+                                scan_index_base=base_idx, n_scans_total=total_scans)
+        if comm is not None:
+            comm.allreduce_plan_stats(plan)
+
+    def step_e2e():
+        out = plan.zerospan_batch(host, N_SCANS, GAIN, XRES, "MAX", rows=None, want_hm=True,
+                                  scan_index_base=base_idx, n_scans_total=total_scans)
+        if comm is not None:
+            comm.allreduce_host(out["max"], out["min"], out["avg"])
+        return out
+
+    # ---- device-resident timing -----------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = plan.launch_count()
+    plan.timer_start()
+    for _ in range(args.steps):
+        step_dev()
+    ms = plan.timer_stop()
+    barrier()
+    launches = plan.launch_count() - l0
+    clocks = sampler.summary()
+    kt = plan.kernel_times(min(args.steps, 64))
+    ms_all = _max_over_ranks(ms, dist, local)
+    value = world * N_SCANS * S * args.steps / (ms_all * 1e-3) / 1e6
+
+    # ---- end to end -----------------------------------------------------------------------------------------------
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = step_e2e()
+    plan.sync()
+    e2e_s = time.perf_counter() - t0
+    e2e_s = _max_over_ranks(e2e_s, dist, local)
+    e2e_value = world * N_SCANS * S * args.steps / e2e_s / 1e6
+    h2d = N_SCANS * S * 8
+    d2h = N_SCANS * XRES * 8 + 3 * F * 8
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        k_ms = float(np.mean(kt)) if kt else ms / args.steps
+        ach = algorithmic_bytes(N_SCANS) / (k_ms * 1e-3) / 1e9
+        # cpu baseline: bounded sample, all host cores
+        cores = min(os.cpu_count() or 1, 64)
+        cpu_v = cpu_reference(cores, 640, reps=2)
+        cpu_1 = cpu_reference(1, 640)
+        line = {
+            "metric": "IQ Msamples/s via window+FFT+max/min/avg at fftSize 2048", "value": value, "unit": "Msamples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_all / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "l2": "input %.2f GiB per step >> 126 MB L2, no flush needed" % (N_SCANS * S * 8 / 2 ** 30),
+                       "frames_per_s": value * 1e6 * info.n_frames / S, "parallelism": "scan-range shards x%d" % world,
+                       "cta_threads": info.cta_threads, "ctas_per_sm": info.ctas_per_sm, "smem_bytes": info.smem_bytes},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "peak_source": peak_src, "kernel": "curscan_smem_kernel<float,C64,11>", "kernel_ms": k_ms,
+                         "algorithmic_bytes_per_launch": algorithmic_bytes(N_SCANS)},
+            "cpu_baseline": {"value": cpu_v, "unit": "Msamples/s", "cores": cores, "kind": "port", "single_core_value": cpu_1,
+                             "sample": "%d scans per process x %d processes (%.0f M IQ samples), best of 2, numpy float64 oracle port" % (640, cores, 640 * cores * S / 1e6)},
+            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    plan.dev_free(d_samples)
+    plan.close()
+    return 0
+
+
+def _max_over_ranks(v, dist, local):
+    if dist is None:
+        return v
+    import torch
+    t = torch.tensor([v], dtype=torch.float64, device="cuda:%d" % local)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _make_comm(world, rank, local, dist):
+    import torch
+    from kspec.comm import Comm
+    uid = Comm.unique_id() if rank == 0 else bytes(128)
+    t = torch.tensor(list(uid), dtype=torch.uint8, device="cuda:%d" % local)
+    dist.broadcast(t, 0)
+    return Comm(world, rank, bytes(t.cpu().tolist()), local)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

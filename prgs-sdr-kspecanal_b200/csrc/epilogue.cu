@@ -1,0 +1,232 @@
+// epilogue.cu — the small per-bin kernels around the fused scan kernel.
+//
+//   stats_finish     zero_span's cross-scan Max/Min/Avg (K:471-476) from per-team partials; Avg is the halving
+//                    recurrence of data_cumu (K:137-139) replayed in float64 over the rows that can still matter.
+//   scan_stitch      _scan_range's overlap stitch and Max/Min/Avg update (K:643-668), closed form per bin.
+//   plotcompress     _data_plotcompress (K:184-200).
+//   linear_epilogue  dB / stats / waterfall for engines that deliver one linear accumulation row per scan.
+//   widen / narrow   T <-> float64 at the ABI boundary.
+#include "kspec_internal.h"
+#include <math.h>
+
+namespace kspec {
+
+namespace {
+
+__device__ __forceinline__ double d_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+
+template <typename T>
+__global__ void stats_finish_kernel(const T* __restrict__ wsMax, const T* __restrict__ wsMin, int slots,
+                                    const T* __restrict__ avgRows, int avgWin, int F, const double* __restrict__ carry,
+                                    int firstIsSeed, double avgScale, double* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= F) return;
+    double mx = carry ? carry[j] : -d_inf();
+    double mn = carry ? carry[F + j] : d_inf();
+    for (int s = 0; s < slots; ++s) {
+        mx = fmax(mx, (double)wsMax[(int64_t)s * F + j]);
+        mn = fmin(mn, (double)wsMin[(int64_t)s * F + j]);
+    }
+    double a;
+    int r = 0;
+    if (carry) a = carry[2 * F + j];
+    else if (firstIsSeed) { a = (double)avgRows[j]; r = 1; }
+    else a = 0.0;
+    for (; r < avgWin; ++r) a = (a + (double)avgRows[(int64_t)r * F + j]) / 2;
+    out[j] = mx;
+    out[F + j] = mn;
+    out[2 * F + j] = (avgScale == 0.0) ? 0.0 : a * avgScale;
+}
+
+template <typename T> __global__ void widen_kernel(const T* __restrict__ s, double* __restrict__ d, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d[i] = (double)s[i];
+}
+template <typename T> __global__ void narrow_kernel(const double* __restrict__ s, T* __restrict__ d, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d[i] = (T)s[i];
+}
+
+template <typename T>
+__global__ void scan_stitch_kernel(const T* __restrict__ rows, const uint8_t* __restrict__ ok, const int64_t* __restrict__ iStart,
+                                   const int64_t* __restrict__ iDone, int nSteps, int F, int64_t total, double failValue,
+                                   int baseIsRaw, int passIndex, double* __restrict__ cur, double* __restrict__ mx,
+                                   double* __restrict__ mn, double* __restrict__ av) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= total) return;
+    // i1 = last step with iStart <= b ; i0 = first step with iStart + F > b  (iStart is non-decreasing)
+    int lo = 0, hi = nSteps;            // upper_bound(iStart, b)
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (iStart[mid] <= b) lo = mid + 1; else hi = mid; }
+    const int i1 = lo - 1;
+    lo = 0; hi = nSteps;                // first with iStart > b - F
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (iStart[mid] + F > b) hi = mid; else lo = mid + 1; }
+    const int i0 = lo;
+    if (i1 < 0 || i0 > i1) return;
+    auto val = [&](int i) -> double {
+        if (ok && !ok[i]) return failValue;
+        return (double)rows[(int64_t)i * F + (b - iStart[i])];
+    };
+    double c = val(i0);
+    for (int i = i0 + 1; i <= i1; ++i) c = (c + val(i)) / 2;     // RAW for the first cover, halving AVG afterwards (K:643-650)
+    cur[b] = c;
+    if (baseIsRaw) {                                            // K:651-656: every covering step updates the stats with its own row
+        double m1 = mx[b], m2 = mn[b], a = av[b];
+        for (int i = i0; i <= i1; ++i) {
+            const double v = val(i);
+            m1 = fmax(m1, v); m2 = fmin(m2, v);
+            a = (passIndex == 0) ? v : (a + v) / 2;
+        }
+        mx[b] = m1; mn[b] = m2; av[b] = a;
+    } else if (b < iDone[i1]) {                                 // K:657-668: slice [iStart:iDone) of the finished Fft.Cur
+        mx[b] = fmax(mx[b], c);
+        mn[b] = fmin(mn[b], c);
+        av[b] = (passIndex == 0) ? c : (av[b] + c) / 2;
+    }
+}
+
+__global__ void plotcompress_kernel(const double* __restrict__ y, int64_t g, int mode, double* __restrict__ out) {
+    __shared__ double sh[256];
+    const int64_t w = blockIdx.x;
+    const double* p = y + w * g;
+    double r = (mode == KSPEC_COMPRESS_MAX) ? -d_inf() : (mode == KSPEC_COMPRESS_MIN ? d_inf() : 0.0);
+    for (int64_t q = threadIdx.x; q < g; q += blockDim.x) {
+        const double v = p[q];
+        r = (mode == KSPEC_COMPRESS_MAX) ? fmax(r, v) : (mode == KSPEC_COMPRESS_MIN ? fmin(r, v) : r + v);
+    }
+    sh[threadIdx.x] = r;
+    __syncthreads();
+    for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+            const double a = sh[threadIdx.x], c = sh[threadIdx.x + s];
+            sh[threadIdx.x] = (mode == KSPEC_COMPRESS_MAX) ? fmax(a, c) : (mode == KSPEC_COMPRESS_MIN ? fmin(a, c) : a + c);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[w] = (mode == KSPEC_COMPRESS_AVG) ? sh[0] / (double)g : sh[0];
+}
+
+__device__ __forceinline__ float db_of(float v) { return 10.0f * log10f(v); }
+__device__ __forceinline__ double db_of(double v) { return 10.0 * log10(v); }
+
+// one thread per shifted bin j; loops over the scans of the batch in order
+template <typename T>
+__global__ void linear_epilogue_kernel(const ScanParams p, const T* __restrict__ acc, int F) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= F) return;
+    // np.fft.fftshift (K:396) rolls by F//2:  out = concat(in[ceil(F/2):], in[:ceil(F/2)])  ->  out[j] = in[(j + ceil(F/2)) mod F]
+    const int c2 = (F + 1) / 2;
+    const int src = (j + c2) % F;
+    T* rows = reinterpret_cast<T*>(p.rows);
+    T mx = 0, mn = 0;
+    for (int64_t s = 0; s < p.nScans; ++s) {
+        T lin = acc[s * F + src] * (T)p.linScale;
+        if (p.rowsKind == KSPEC_ROWS_LINEAR) rows[s * F + j] = lin;
+        if (p.rowsKind == KSPEC_ROWS_DB || p.wantStats) {
+            if (p.dbClip) lin = fmax(lin, (T)p.minAmp);
+            T db = db_of(lin) - (T)p.gain;
+            if (p.infToZero && isinf(db)) db = (T)0;
+            if (p.rowsKind == KSPEC_ROWS_DB) rows[s * F + j] = db;
+            if (p.wantStats) {
+                mx = (s == 0) ? db : fmax(mx, db);
+                mn = (s == 0) ? db : fmin(mn, db);
+                const int64_t ar = s - (p.nScans - p.avgWin);
+                if (ar >= 0) reinterpret_cast<T*>(p.avgRows)[ar * F + j] = db;
+            }
+        }
+    }
+    if (p.wantStats) {
+        reinterpret_cast<T*>(p.wsMax)[j] = mx;
+        reinterpret_cast<T*>(p.wsMin)[j] = mn;
+    }
+}
+
+// waterfall rows for the linear engines: block per (scan, output column)
+template <typename T>
+__global__ void linear_hm_kernel(const ScanParams p, const T* __restrict__ acc, int F) {
+    __shared__ T sh[256];
+    const int W = p.hmW, g = F / W;
+    const int64_t s = blockIdx.x / W;
+    const int w = blockIdx.x % W;
+    const int c2 = (F + 1) / 2;
+    const int mode = p.hmMode;
+    const T inf = (T)d_inf();
+    T r = (mode == KSPEC_COMPRESS_MAX) ? -inf : (mode == KSPEC_COMPRESS_MIN ? inf : (T)0);
+    for (int q = threadIdx.x; q < g; q += blockDim.x) {
+        const int j = w * g + q;
+        T lin = acc[s * F + (j + c2) % F] * (T)p.linScale;
+        if (p.dbClip) lin = fmax(lin, (T)p.minAmp);
+        T db = db_of(lin) - (T)p.gain;
+        if (p.infToZero && isinf(db)) db = (T)0;
+        if (p.adj) db -= reinterpret_cast<const T*>(p.adj)[j];
+        r = (mode == KSPEC_COMPRESS_MAX) ? fmax(r, db) : (mode == KSPEC_COMPRESS_MIN ? fmin(r, db) : r + db);
+    }
+    sh[threadIdx.x] = r;
+    __syncthreads();
+    for (int st = blockDim.x >> 1; st > 0; st >>= 1) {
+        if ((int)threadIdx.x < st) {
+            const T a = sh[threadIdx.x], c = sh[threadIdx.x + st];
+            sh[threadIdx.x] = (mode == KSPEC_COMPRESS_MAX) ? fmax(a, c) : (mode == KSPEC_COMPRESS_MIN ? fmin(a, c) : a + c);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        T v = sh[0];
+        if (mode == KSPEC_COMPRESS_AVG) v /= (T)g;
+        reinterpret_cast<T*>(p.hm)[s * W + w] = v;
+    }
+}
+
+inline int nblk(int64_t n, int t) { return (int)((n + t - 1) / t); }
+
+}  // namespace
+
+void launch_stats_finish(int prec, const void* wsMax, const void* wsMin, int slots, const void* avgRows, int avgWin, int F,
+                         const double* carry, int firstIsSeed, double avgScale, double* out, cudaStream_t st) {
+    if (prec == KSPEC_PREC_F32)
+        stats_finish_kernel<float><<<nblk(F, 128), 128, 0, st>>>((const float*)wsMax, (const float*)wsMin, slots,
+                                                                 (const float*)avgRows, avgWin, F, carry, firstIsSeed, avgScale, out);
+    else
+        stats_finish_kernel<double><<<nblk(F, 128), 128, 0, st>>>((const double*)wsMax, (const double*)wsMin, slots,
+                                                                  (const double*)avgRows, avgWin, F, carry, firstIsSeed, avgScale, out);
+}
+
+void launch_widen(int prec, const void* src, double* dst, int64_t n, cudaStream_t st) {
+    if (n <= 0) return;
+    const int g = (int)(n / 256 + 1 < 4096 ? n / 256 + 1 : 4096);
+    if (prec == KSPEC_PREC_F32) widen_kernel<float><<<g, 256, 0, st>>>((const float*)src, dst, n);
+    else widen_kernel<double><<<g, 256, 0, st>>>((const double*)src, dst, n);
+}
+
+void launch_narrow(int prec, const double* src, void* dst, int64_t n, cudaStream_t st) {
+    if (n <= 0) return;
+    const int g = (int)(n / 256 + 1 < 4096 ? n / 256 + 1 : 4096);
+    if (prec == KSPEC_PREC_F32) narrow_kernel<float><<<g, 256, 0, st>>>(src, (float*)dst, n);
+    else narrow_kernel<double><<<g, 256, 0, st>>>(src, (double*)dst, n);
+}
+
+void launch_scan_stitch(int prec, const void* dbRows, const uint8_t* stepOk, const int64_t* iStart, const int64_t* iDone,
+                        int nSteps, int F, int64_t total, double failValue, int baseIsRaw, int passIndex, double* cur,
+                        double* mx, double* mn, double* av, cudaStream_t st) {
+    if (prec == KSPEC_PREC_F32)
+        scan_stitch_kernel<float><<<nblk(total, 256), 256, 0, st>>>((const float*)dbRows, stepOk, iStart, iDone, nSteps, F, total,
+                                                                    failValue, baseIsRaw, passIndex, cur, mx, mn, av);
+    else
+        scan_stitch_kernel<double><<<nblk(total, 256), 256, 0, st>>>((const double*)dbRows, stepOk, iStart, iDone, nSteps, F,
+                                                                     total, failValue, baseIsRaw, passIndex, cur, mx, mn, av);
+}
+
+void launch_plotcompress(const double* y, int64_t n, int xRes, int mode, double* out, cudaStream_t st) {
+    const int64_t g = n / xRes;
+    plotcompress_kernel<<<xRes, 256, 0, st>>>(y, g, mode, out);
+}
+
+void launch_linear_epilogue(int prec, const ScanParams& p, const void* acc, int F, int slots, cudaStream_t st) {
+    (void)slots;
+    if (prec == KSPEC_PREC_F32) {
+        linear_epilogue_kernel<float><<<nblk(F, 256), 256, 0, st>>>(p, (const float*)acc, F);
+        if (p.hm) linear_hm_kernel<float><<<(unsigned)(p.nScans * p.hmW), 256, 0, st>>>(p, (const float*)acc, F);
+    } else {
+        linear_epilogue_kernel<double><<<nblk(F, 256), 256, 0, st>>>(p, (const double*)acc, F);
+        if (p.hm) linear_hm_kernel<double><<<(unsigned)(p.nScans * p.hmW), 256, 0, st>>>(p, (const double*)acc, F);
+    }
+}
+
+}  // namespace kspec

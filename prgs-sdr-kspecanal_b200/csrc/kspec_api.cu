@@ -1,0 +1,625 @@
+// kspec_api.cu — the C ABI of libkspec.so (include/kspec.h): plans, batches, device buffers, timers.
+// Host-side orchestration only; the arithmetic lives in curscan_smem.cuh, bigfft.cu and epilogue.cu.
+#include "kspec_internal.h"
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+
+namespace kspec {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);   \
+            return e_ == cudaErrorMemoryAllocation ? KSPEC_ERR_NOMEM : KSPEC_ERR_CUDA;               \
+        }                                                                                            \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return KSPEC_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + (bytes >> 3);      // grow-only with slack: repeated batches reuse the allocation
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e != cudaSuccess) {
+            set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+            cudaGetLastError();
+            return KSPEC_ERR_NOMEM;
+        }
+        cap = want;
+        return KSPEC_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace kspec
+
+using namespace kspec;
+
+struct kspec_plan {
+    int F = 0;
+    int64_t S = 0;
+    double r = 0;
+    int cumu = 0, inFmt = 0, prec = 0, device = 0, path = 0, log2F = -1;
+    double u8off = 0, u8scale = 0, winAdj = 0, linScale = 0;
+    std::vector<int64_t> offs;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int smCount = 0;
+    SmemKernelInfo ki{};
+    int64_t convSize = 0;
+    BigFft* big = nullptr;
+    int64_t launches = 0;
+    // event pairs around the most recent engine launches (bench: per-kernel duration for the roofline)
+    static constexpr int KT = 64;
+    cudaEvent_t kev[KT][2] = {};
+    int64_t kcount = 0;
+    // device tables
+    int32_t* dOffs = nullptr;
+    void* dWin = nullptr;
+    void* dTw = nullptr;
+    // grow-only workspaces
+    DevBuf in, rows, hm, wsMax, wsMin, avgRows, adj, adj64, carry, stats, wide, acc, l2, misc;
+    // what the last *_dev batch left behind (for fetch)
+    int64_t lastScans = 0;
+    int lastRowsKind = 0, lastW = 0;
+    bool lastHm = false, haveBatch = false;
+};
+
+namespace {
+
+size_t in_elem_bytes(int fmt) { return fmt == KSPEC_IN_U8_IQ ? 2 : (fmt == KSPEC_IN_C64 ? 8 : 16); }
+size_t real_bytes(int prec) { return prec == KSPEC_PREC_F32 ? 4 : 8; }
+
+int launch_smem(const kspec_plan* pl, const ScanParams& p, int grid, SmemKernelInfo* info) {
+    const bool f32 = pl->prec == KSPEC_PREC_F32;
+    switch (pl->inFmt) {
+        case KSPEC_IN_U8_IQ: return f32 ? launch_smem_f32_u8(pl->log2F, p, grid, pl->st, info) : launch_smem_f64_u8(pl->log2F, p, grid, pl->st, info);
+        case KSPEC_IN_C64:   return f32 ? launch_smem_f32_c64(pl->log2F, p, grid, pl->st, info) : launch_smem_f64_c64(pl->log2F, p, grid, pl->st, info);
+        default:             return f32 ? launch_smem_f32_c128(pl->log2F, p, grid, pl->st, info) : launch_smem_f64_c128(pl->log2F, p, grid, pl->st, info);
+    }
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+ScanParams base_params(const kspec_plan* pl, const void* dSamples, int64_t nScans) {
+    ScanParams p{};
+    p.samples = dSamples;
+    p.scanStride = pl->S;
+    p.nScans = nScans;
+    p.frameOffs = pl->dOffs;
+    p.nFrames = (int)pl->offs.size();
+    p.win = pl->dWin;
+    p.tw = pl->dTw;
+    p.cumuMode = pl->cumu;
+    p.linScale = pl->linScale;
+    p.u8Offset = pl->u8off;
+    p.u8Scale = pl->u8scale;
+    p.hmMode = KSPEC_COMPRESS_RAW;
+    return p;
+}
+
+// run the FFT engine + per-scan epilogue described by p (rows/stats/hm pointers already set); slots out
+int run_engine(kspec_plan* pl, ScanParams& p, int* slotsOut) {
+    const size_t rb = real_bytes(pl->prec);
+    if (pl->path == KSPEC_PATH_SMEM) {
+        const int teams = pl->ki.teams;
+        int64_t need = (p.nScans + teams - 1) / teams;
+        int64_t cap = (int64_t)pl->smCount * (pl->ki.ctasPerSm > 0 ? pl->ki.ctasPerSm : 1);
+        int grid = (int)(need < cap ? need : cap);
+        if (grid < 1) grid = 1;
+        const int slots = grid * teams;
+        if (p.wantStats) {
+            int rc;
+            if ((rc = pl->wsMax.reserve((size_t)slots * pl->F * rb))) return rc;
+            if ((rc = pl->wsMin.reserve((size_t)slots * pl->F * rb))) return rc;
+            p.wsMax = pl->wsMax.p;
+            p.wsMin = pl->wsMin.p;
+        }
+        const int ks = (int)(pl->kcount % kspec_plan::KT);
+        cudaEventRecord(pl->kev[ks][0], pl->st);
+        int e = launch_smem(pl, p, grid, nullptr);
+        cudaEventRecord(pl->kev[ks][1], pl->st);
+        pl->kcount += 1;
+        if (e != 0) { set_error("scan kernel launch failed: %s", cudaGetErrorString((cudaError_t)e)); return KSPEC_ERR_CUDA; }
+        pl->launches += 1;
+        *slotsOut = slots;
+        return KSPEC_OK;
+    }
+    // big engines: un-normalised accumulation rows, then a shared epilogue
+    int rc;
+    if ((rc = pl->acc.reserve((size_t)p.nScans * pl->F * rb))) return rc;
+    if (p.wantStats) {
+        if ((rc = pl->wsMax.reserve((size_t)pl->F * rb))) return rc;
+        if ((rc = pl->wsMin.reserve((size_t)pl->F * rb))) return rc;
+        p.wsMax = pl->wsMax.p;
+        p.wsMin = pl->wsMin.p;
+    }
+    rc = bigfft_run(pl->big, p.samples, pl->S, p.nScans, pl->offs.data(), (int)pl->offs.size(), pl->cumu, pl->acc.p, &pl->launches);
+    if (rc) return rc;
+    launch_linear_epilogue(pl->prec, p, pl->acc.p, pl->F, 1, pl->st);
+    pl->launches += p.hm ? 2 : 1;
+    *slotsOut = 1;
+    return KSPEC_OK;
+}
+
+int check_plan(const kspec_plan* pl) {
+    if (!pl) { set_error("null plan"); return KSPEC_ERR_ARG; }
+    return KSPEC_OK;
+}
+
+int hm_width(int F, int xRes, int hmMode) { return (hmMode != KSPEC_COMPRESS_RAW && F > xRes) ? xRes : F; }
+
+}  // namespace
+
+extern "C" {
+
+int kspec_version(void) { return KSPEC_VERSION; }
+const char* kspec_last_error(void) { return g_err; }
+
+int kspec_device_count(int* n) {
+    if (!n) { set_error("null argument"); return KSPEC_ERR_ARG; }
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) { cudaGetLastError(); *n = 0; set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e)); return KSPEC_ERR_CUDA; }
+    *n = c;
+    return KSPEC_OK;
+}
+
+int kspec_plan_create(kspec_plan** out, int fftSize, int64_t fullSize, double nonOverlap, int cumuMode, const double* window,
+                      int inFmt, double u8_offset, double u8_scale, int precision, int device) {
+    if (!out || !window) { set_error("null argument"); return KSPEC_ERR_ARG; }
+    *out = nullptr;
+    if (fftSize < 1 || fullSize < fftSize) { set_error("fftSize %d / fullSize %lld invalid", fftSize, (long long)fullSize); return KSPEC_ERR_ARG; }
+    if (!(nonOverlap > 0.0)) { set_error("curScanNonOverlap must be > 0"); return KSPEC_ERR_ARG; }
+    if (cumuMode < KSPEC_CUMU_RAW || cumuMode > KSPEC_CUMU_MIN) { set_error("unknown cumuMode %d", cumuMode); return KSPEC_ERR_ARG; }
+    if (inFmt < KSPEC_IN_U8_IQ || inFmt > KSPEC_IN_C128) { set_error("unknown ingest format %d", inFmt); return KSPEC_ERR_ARG; }
+    if (precision < KSPEC_PREC_AUTO || precision > KSPEC_PREC_F64) { set_error("unknown precision %d", precision); return KSPEC_ERR_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device: libkspec has no CPU fallback");
+        return KSPEC_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { set_error("device %d out of range (%d devices)", device, ndev); return KSPEC_ERR_ARG; }
+
+    kspec_plan* pl = new (std::nothrow) kspec_plan();
+    if (!pl) { set_error("out of host memory"); return KSPEC_ERR_NOMEM; }
+    pl->F = fftSize; pl->S = fullSize; pl->r = nonOverlap; pl->cumu = cumuMode; pl->inFmt = inFmt; pl->device = device;
+    pl->u8off = u8_offset; pl->u8scale = u8_scale;
+    const bool pow2 = (fftSize & (fftSize - 1)) == 0;
+    if (pow2) { int l = 0; while ((1 << l) < fftSize) ++l; pl->log2F = l; }
+    if (precision == KSPEC_PREC_AUTO) precision = (pow2 && fftSize <= 4096) ? KSPEC_PREC_F32 : KSPEC_PREC_F64;
+    pl->prec = precision;
+    const int smemMax = precision == KSPEC_PREC_F32 ? SMEM_MAX_LOG2F_F32 : SMEM_MAX_LOG2F_F64;
+    if (pow2 && pl->log2F >= SMEM_MIN_LOG2F && pl->log2F <= smemMax) pl->path = KSPEC_PATH_SMEM;
+    else if (pow2 && pl->log2F > smemMax) pl->path = KSPEC_PATH_FOURSTEP;
+    else pl->path = KSPEC_PATH_BLUESTEIN;
+
+    // frame offsets: int(i*F*r) with the product evaluated left to right in float64 (K:368, K:386-390)
+    const int64_t nLoops = (int64_t)((double)fullSize / ((double)fftSize * nonOverlap));
+    for (int64_t i = 0; i < nLoops; ++i) {
+        const int64_t start = (int64_t)(((double)i * (double)fftSize) * nonOverlap);
+        if (start + fftSize > fullSize) break;
+        pl->offs.push_back(start);
+    }
+    if (pl->offs.empty()) { delete pl; set_error("no complete frame fits (fullSize %lld, fftSize %d, nonOverlap %g)", (long long)fullSize, fftSize, nonOverlap); return KSPEC_ERR_ARG; }
+    double sum = 0.0;                                        // np.sum is pairwise; plain summation differs by < 1e-13 relative
+    {   // pairwise summation to stay within an ulp or two of numpy's np.sum (K:373)
+        std::vector<double> t(window, window + fftSize);
+        size_t n = t.size();
+        while (n > 1) { size_t h = n / 2; for (size_t i = 0; i < h; ++i) t[i] = t[2 * i] + t[2 * i + 1]; if (n & 1) { t[h] = t[n - 1]; n = h + 1; } else n = h; }
+        sum = t[0];
+    }
+    pl->winAdj = (double)fftSize / sum;
+    pl->linScale = pl->winAdj * 2.0 / (double)fftSize;
+
+    DeviceGuard guard(device);
+    auto fail = [&](int rc) { kspec_plan_destroy(pl); return rc; };
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { set_error("cudaGetDeviceProperties failed"); return fail(KSPEC_ERR_CUDA); }
+    pl->smCount = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&pl->st, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&pl->ev0) != cudaSuccess ||
+        cudaEventCreate(&pl->ev1) != cudaSuccess) {
+        set_error("stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail(KSPEC_ERR_CUDA);
+    }
+    for (int i = 0; i < kspec_plan::KT; ++i)
+        if (cudaEventCreate(&pl->kev[i][0]) != cudaSuccess || cudaEventCreate(&pl->kev[i][1]) != cudaSuccess) {
+            set_error("event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return fail(KSPEC_ERR_CUDA);
+        }
+    const size_t rb = real_bytes(precision);
+    if (pl->path == KSPEC_PATH_SMEM) {
+        std::vector<int32_t> o32(pl->offs.begin(), pl->offs.end());
+        if (cudaMalloc(&pl->dOffs, o32.size() * 4) != cudaSuccess || cudaMalloc(&pl->dWin, fftSize * rb) != cudaSuccess ||
+            cudaMalloc(&pl->dTw, (size_t)fftSize * 2 * rb) != cudaSuccess) {
+            set_error("table allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return fail(KSPEC_ERR_NOMEM);
+        }
+        cudaMemcpy(pl->dOffs, o32.data(), o32.size() * 4, cudaMemcpyHostToDevice);
+        // twiddles exp(-2 pi i k / F): computed in float64 with exact octant symmetry, rounded once to T
+        std::vector<double> tw(2 * (size_t)fftSize);
+        for (int k = 0; k < fftSize; ++k) {
+            const double a = -2.0 * M_PI * (double)k / (double)fftSize;
+            tw[2 * k] = cos(a);
+            tw[2 * k + 1] = sin(a);
+        }
+        if (fftSize >= 4) { tw[2 * (fftSize / 4)] = 0.0; tw[2 * (fftSize / 4) + 1] = -1.0; tw[2 * (fftSize / 2)] = -1.0; tw[2 * (fftSize / 2) + 1] = 0.0;
+                            tw[2 * (3 * fftSize / 4)] = 0.0; tw[2 * (3 * fftSize / 4) + 1] = 1.0; }
+        if (precision == KSPEC_PREC_F32) {
+            std::vector<float> w32(fftSize), t32(2 * (size_t)fftSize);
+            for (int i = 0; i < fftSize; ++i) w32[i] = (float)window[i];
+            for (size_t i = 0; i < t32.size(); ++i) t32[i] = (float)tw[i];
+            cudaMemcpy(pl->dWin, w32.data(), fftSize * 4, cudaMemcpyHostToDevice);
+            cudaMemcpy(pl->dTw, t32.data(), t32.size() * 4, cudaMemcpyHostToDevice);
+        } else {
+            cudaMemcpy(pl->dWin, window, fftSize * 8, cudaMemcpyHostToDevice);
+            cudaMemcpy(pl->dTw, tw.data(), tw.size() * 8, cudaMemcpyHostToDevice);
+        }
+        ScanParams dummy{};
+        if (launch_smem(pl, dummy, 0, &pl->ki) != 0) { set_error("kernel attribute query failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(KSPEC_ERR_CUDA); }
+        if (pl->ki.ctasPerSm < 1) { set_error("fused kernel for fftSize %d does not fit on this device", fftSize); return fail(KSPEC_ERR_UNSUPPORTED); }
+    } else {
+        char err[256] = "";
+        pl->big = bigfft_create(precision, inFmt, fftSize, pl->path, &pl->convSize, window, u8_offset, u8_scale, pl->st, err, sizeof(err));
+        if (!pl->big) { set_error("big-FFT engine: %s", err); return fail(KSPEC_ERR_UNSUPPORTED); }
+    }
+    if (cudaDeviceSynchronize() != cudaSuccess) { set_error("plan setup failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(KSPEC_ERR_CUDA); }
+    *out = pl;
+    return KSPEC_OK;
+}
+
+int kspec_plan_destroy(kspec_plan* pl) {
+    if (!pl) return KSPEC_OK;
+    DeviceGuard guard(pl->device);
+    if (pl->st) cudaStreamSynchronize(pl->st);
+    if (pl->big) bigfft_destroy(pl->big);
+    for (DevBuf* b : {&pl->in, &pl->rows, &pl->hm, &pl->wsMax, &pl->wsMin, &pl->avgRows, &pl->adj, &pl->adj64, &pl->carry, &pl->stats,
+                      &pl->wide, &pl->acc, &pl->l2, &pl->misc}) b->release();
+    if (pl->dOffs) cudaFree(pl->dOffs);
+    if (pl->dWin) cudaFree(pl->dWin);
+    if (pl->dTw) cudaFree(pl->dTw);
+    for (int i = 0; i < kspec_plan::KT; ++i) { if (pl->kev[i][0]) cudaEventDestroy(pl->kev[i][0]); if (pl->kev[i][1]) cudaEventDestroy(pl->kev[i][1]); }
+    if (pl->ev0) cudaEventDestroy(pl->ev0);
+    if (pl->ev1) cudaEventDestroy(pl->ev1);
+    if (pl->st) cudaStreamDestroy(pl->st);
+    delete pl;
+    return KSPEC_OK;
+}
+
+int kspec_plan_frames(const kspec_plan* pl, int64_t* offsets, int* n) {
+    if (check_plan(pl) || !n) { set_error("null argument"); return KSPEC_ERR_ARG; }
+    if (offsets) memcpy(offsets, pl->offs.data(), pl->offs.size() * sizeof(int64_t));
+    *n = (int)pl->offs.size();
+    return KSPEC_OK;
+}
+
+int kspec_plan_info(const kspec_plan* pl, kspec_plan_info_t* info) {
+    if (check_plan(pl) || !info) { set_error("null argument"); return KSPEC_ERR_ARG; }
+    memset(info, 0, sizeof(*info));
+    info->fft_size = pl->F; info->full_size = pl->S; info->n_frames = (int)pl->offs.size(); info->precision = pl->prec;
+    info->path = pl->path; info->in_fmt = pl->inFmt; info->device = pl->device; info->sm_count = pl->smCount;
+    info->cta_threads = pl->ki.ctaThreads; info->ctas_per_sm = pl->ki.ctasPerSm; info->smem_bytes = pl->ki.smemBytes;
+    info->scans_per_cta = pl->ki.teams; info->conv_size = pl->convSize; info->win_adj = pl->winAdj;
+    return KSPEC_OK;
+}
+
+// ---- device-resident batch ---------------------------------------------------------------------------------------
+int kspec_zerospan_batch_dev(kspec_plan* pl, const void* dSamples, int64_t nScans, double gain, const double* adj, int hmMode,
+                             int xRes, int rowsKind, int wantHm, const double* mx, const double* mn, const double* av, int carry,
+                             int64_t scanIndexBase, int64_t nScansTotal) {
+    if (check_plan(pl)) return KSPEC_ERR_ARG;
+    if (!dSamples || nScans < 1) { set_error("no scans"); return KSPEC_ERR_ARG; }
+    if (rowsKind < KSPEC_ROWS_NONE || rowsKind > KSPEC_ROWS_DB) { set_error("unknown rowsKind %d", rowsKind); return KSPEC_ERR_ARG; }
+    if (hmMode < KSPEC_COMPRESS_RAW || hmMode > KSPEC_COMPRESS_MIN) { set_error("unknown pltCompressHM %d", hmMode); return KSPEC_ERR_ARG; }
+    if (carry && (!mx || !mn || !av)) { set_error("carry requested without max/min/avg state"); return KSPEC_ERR_ARG; }
+    if (nScansTotal < scanIndexBase + nScans || scanIndexBase < 0) { set_error("shard [%lld,+%lld) outside capture of %lld scans", (long long)scanIndexBase, (long long)nScans, (long long)nScansTotal); return KSPEC_ERR_ARG; }
+    const int F = pl->F;
+    const int W = hm_width(F, xRes, hmMode);
+    if (wantHm && (xRes < 1 || F % W != 0)) { set_error("fftSize %d is not a multiple of the waterfall width %d (xRes must divide fftSize, K:941-949)", F, W); return KSPEC_ERR_ARG; }
+    DeviceGuard guard(pl->device);
+    const size_t rb = real_bytes(pl->prec);
+    int rc;
+    ScanParams p = base_params(pl, dSamples, nScans);
+    p.gain = gain;
+    p.rowsKind = rowsKind;
+    if (rowsKind != KSPEC_ROWS_NONE) { if ((rc = pl->rows.reserve((size_t)nScans * F * rb))) return rc; p.rows = pl->rows.p; }
+    if (wantHm) { if ((rc = pl->hm.reserve((size_t)nScans * W * rb))) return rc; p.hm = pl->hm.p; p.hmMode = hmMode; p.hmW = W; }
+    p.wantStats = 1;
+    p.avgWin = (int)(nScans < AVG_WINDOW ? nScans : AVG_WINDOW);
+    if ((rc = pl->avgRows.reserve((size_t)p.avgWin * F * rb))) return rc;
+    p.avgRows = pl->avgRows.p;
+    if (adj) {
+        if ((rc = pl->adj64.reserve((size_t)F * 8)) || (rc = pl->adj.reserve((size_t)F * rb))) return rc;
+        CK(cudaMemcpyAsync(pl->adj64.p, adj, (size_t)F * 8, cudaMemcpyHostToDevice, pl->st));
+        launch_narrow(pl->prec, (const double*)pl->adj64.p, pl->adj.p, F, pl->st);
+        pl->launches += 1;
+        p.adj = pl->adj.p;
+    }
+    if ((rc = pl->stats.reserve((size_t)3 * F * 8))) return rc;
+    const double* dCarry = nullptr;
+    if (carry) {
+        if ((rc = pl->carry.reserve((size_t)3 * F * 8))) return rc;
+        CK(cudaMemcpyAsync(pl->carry.p, mx, (size_t)F * 8, cudaMemcpyHostToDevice, pl->st));
+        CK(cudaMemcpyAsync((double*)pl->carry.p + F, mn, (size_t)F * 8, cudaMemcpyHostToDevice, pl->st));
+        CK(cudaMemcpyAsync((double*)pl->carry.p + 2 * F, av, (size_t)F * 8, cudaMemcpyHostToDevice, pl->st));
+        dCarry = (const double*)pl->carry.p;
+    }
+    int slots = 0;
+    if ((rc = run_engine(pl, p, &slots))) return rc;
+    // Avg: this shard's part of the halving recurrence, pre-weighted for a SUM over shards
+    const int64_t after = nScansTotal - (scanIndexBase + nScans);
+    const double avgScale = after == 0 ? 1.0 : ldexp(1.0, (int)(after > 2000 ? -2000 : -after));
+    const int firstIsSeed = (!carry && scanIndexBase == 0) ? 1 : 0;
+    launch_stats_finish(pl->prec, pl->wsMax.p, pl->wsMin.p, slots, pl->avgRows.p, p.avgWin, F, dCarry, firstIsSeed, avgScale,
+                        (double*)pl->stats.p, pl->st);
+    pl->launches += 1;
+    CK(cudaGetLastError());
+    pl->lastScans = nScans; pl->lastRowsKind = rowsKind; pl->lastW = W; pl->lastHm = wantHm != 0; pl->haveBatch = true;
+    return KSPEC_OK;
+}
+
+int kspec_zerospan_fetch(kspec_plan* pl, double* rows, double* hm_rows, double* mx, double* mn, double* av) {
+    if (check_plan(pl)) return KSPEC_ERR_ARG;
+    if (!pl->haveBatch) { set_error("kspec_zerospan_fetch before any batch"); return KSPEC_ERR_STATE; }
+    DeviceGuard guard(pl->device);
+    const int F = pl->F;
+    int rc;
+    auto copy_rows = [&](const DevBuf& src, int64_t n, double* dst) -> int {
+        if (pl->prec == KSPEC_PREC_F64) {
+            CK(cudaMemcpyAsync(dst, src.p, (size_t)n * 8, cudaMemcpyDeviceToHost, pl->st));
+        } else {
+            if ((rc = pl->wide.reserve((size_t)n * 8))) return rc;
+            launch_widen(pl->prec, src.p, (double*)pl->wide.p, n, pl->st);
+            pl->launches += 1;
+            CK(cudaMemcpyAsync(dst, pl->wide.p, (size_t)n * 8, cudaMemcpyDeviceToHost, pl->st));
+            CK(cudaStreamSynchronize(pl->st));      // `wide` is reused by the next copy
+        }
+        return KSPEC_OK;
+    };
+    if (rows) {
+        if (pl->lastRowsKind == KSPEC_ROWS_NONE) { set_error("rows requested but the batch emitted none"); return KSPEC_ERR_STATE; }
+        if ((rc = copy_rows(pl->rows, pl->lastScans * F, rows))) return rc;
+    }
+    if (hm_rows) {
+        if (!pl->lastHm) { set_error("waterfall rows requested but the batch emitted none"); return KSPEC_ERR_STATE; }
+        if ((rc = copy_rows(pl->hm, pl->lastScans * pl->lastW, hm_rows))) return rc;
+    }
+    const double* s = (const double*)pl->stats.p;
+    if (mx) CK(cudaMemcpyAsync(mx, s, (size_t)F * 8, cudaMemcpyDeviceToHost, pl->st));
+    if (mn) CK(cudaMemcpyAsync(mn, s + F, (size_t)F * 8, cudaMemcpyDeviceToHost, pl->st));
+    if (av) CK(cudaMemcpyAsync(av, s + 2 * F, (size_t)F * 8, cudaMemcpyDeviceToHost, pl->st));
+    CK(cudaStreamSynchronize(pl->st));
+    return KSPEC_OK;
+}
+
+// ---- host-buffer entry points ------------------------------------------------------------------------------------
+int kspec_zerospan_batch(kspec_plan* pl, const void* samples, int64_t nScans, double gain, const double* adj, int hmMode, int xRes,
+                         int rowsKind, double* rows, double* hm_rows, double* mx, double* mn, double* av, int carry,
+                         int64_t scanIndexBase, int64_t nScansTotal) {
+    if (check_plan(pl)) return KSPEC_ERR_ARG;
+    if (!samples || nScans < 1) { set_error("no scans"); return KSPEC_ERR_ARG; }
+    if (rows == nullptr) rowsKind = KSPEC_ROWS_NONE;
+    DeviceGuard guard(pl->device);
+    const size_t bytes = (size_t)nScans * pl->S * in_elem_bytes(pl->inFmt);
+    int rc;
+    if ((rc = pl->in.reserve(bytes))) return rc;
+    CK(cudaMemcpyAsync(pl->in.p, samples, bytes, cudaMemcpyHostToDevice, pl->st));
+    if ((rc = kspec_zerospan_batch_dev(pl, pl->in.p, nScans, gain, adj, hmMode, xRes, rowsKind, hm_rows != nullptr, mx, mn, av, carry,
+                                       scanIndexBase, nScansTotal)))
+        return rc;
+    return kspec_zerospan_fetch(pl, rows, hm_rows, mx, mn, av);
+}
+
+int kspec_curscan(kspec_plan* pl, const void* samples, double* out) {
+    if (check_plan(pl)) return KSPEC_ERR_ARG;
+    if (!samples || !out) { set_error("null argument"); return KSPEC_ERR_ARG; }
+    DeviceGuard guard(pl->device);
+    const int F = pl->F;
+    const size_t rb = real_bytes(pl->prec);
+    const size_t bytes = (size_t)pl->S * in_elem_bytes(pl->inFmt);
+    int rc;
+    if ((rc = pl->in.reserve(bytes)) || (rc = pl->rows.reserve((size_t)F * rb))) return rc;
+    CK(cudaMemcpyAsync(pl->in.p, samples, bytes, cudaMemcpyHostToDevice, pl->st));
+    ScanParams p = base_params(pl, pl->in.p, 1);
+    p.rowsKind = KSPEC_ROWS_LINEAR;
+    p.rows = pl->rows.p;
+    int slots = 0;
+    if ((rc = run_engine(pl, p, &slots))) return rc;
+    if (pl->prec == KSPEC_PREC_F64) {
+        CK(cudaMemcpyAsync(out, pl->rows.p, (size_t)F * 8, cudaMemcpyDeviceToHost, pl->st));
+    } else {
+        if ((rc = pl->wide.reserve((size_t)F * 8))) return rc;
+        launch_widen(pl->prec, pl->rows.p, (double*)pl->wide.p, F, pl->st);
+        pl->launches += 1;
+        CK(cudaMemcpyAsync(out, pl->wide.p, (size_t)F * 8, cudaMemcpyDeviceToHost, pl->st));
+    }
+    CK(cudaStreamSynchronize(pl->st));
+    pl->haveBatch = false;
+    return KSPEC_OK;
+}
+
+int kspec_scan_batch(kspec_plan* pl, const void* samples, int nSteps, const uint8_t* stepOk, const int64_t* iStart, const int64_t* iDone,
+                     int64_t totalEntries, double minAmp4Clip, double gain, int baseIsRaw, int passIndex, double* cur, double* mx,
+                     double* mn, double* av) {
+    if (check_plan(pl)) return KSPEC_ERR_ARG;
+    if (!samples || nSteps < 1 || !iStart || !iDone || !cur || !mx || !mn || !av || totalEntries < 1) { set_error("bad scan batch arguments"); return KSPEC_ERR_ARG; }
+    for (int i = 1; i < nSteps; ++i)
+        if (iStart[i] < iStart[i - 1] || iStart[i] > iStart[i - 1] + pl->F) { set_error("scanRangeNonOverlap must be in (0,1]: step %d starts at %lld after %lld", i, (long long)iStart[i], (long long)iStart[i - 1]); return KSPEC_ERR_ARG; }
+    DeviceGuard guard(pl->device);
+    const int F = pl->F;
+    const size_t rb = real_bytes(pl->prec);
+    const size_t bytes = (size_t)nSteps * pl->S * in_elem_bytes(pl->inFmt);
+    int rc;
+    if ((rc = pl->in.reserve(bytes)) || (rc = pl->rows.reserve((size_t)nSteps * F * rb))) return rc;
+    CK(cudaMemcpyAsync(pl->in.p, samples, bytes, cudaMemcpyHostToDevice, pl->st));
+    ScanParams p = base_params(pl, pl->in.p, nSteps);
+    p.rowsKind = KSPEC_ROWS_DB;
+    p.rows = pl->rows.p;
+    p.dbClip = 1; p.minAmp = minAmp4Clip; p.infToZero = 1; p.gain = gain;
+    int slots = 0;
+    if ((rc = run_engine(pl, p, &slots))) return rc;
+    // geometry + state vectors
+    const size_t geoBytes = (size_t)nSteps * (8 + 8 + 1);
+    const size_t stBytes = (size_t)totalEntries * 8;
+    if ((rc = pl->misc.reserve(geoBytes + 64 + 4 * stBytes))) return rc;
+    char* base = (char*)pl->misc.p;
+    double* dCur = (double*)base;
+    double* dMx = dCur + totalEntries; double* dMn = dMx + totalEntries; double* dAv = dMn + totalEntries;
+    int64_t* dStart = (int64_t*)(dAv + totalEntries);
+    int64_t* dDone = dStart + nSteps;
+    uint8_t* dOk = (uint8_t*)(dDone + nSteps);
+    CK(cudaMemcpyAsync(dCur, cur, stBytes, cudaMemcpyHostToDevice, pl->st));
+    CK(cudaMemcpyAsync(dMx, mx, stBytes, cudaMemcpyHostToDevice, pl->st));
+    CK(cudaMemcpyAsync(dMn, mn, stBytes, cudaMemcpyHostToDevice, pl->st));
+    CK(cudaMemcpyAsync(dAv, av, stBytes, cudaMemcpyHostToDevice, pl->st));
+    CK(cudaMemcpyAsync(dStart, iStart, (size_t)nSteps * 8, cudaMemcpyHostToDevice, pl->st));
+    CK(cudaMemcpyAsync(dDone, iDone, (size_t)nSteps * 8, cudaMemcpyHostToDevice, pl->st));
+    if (stepOk) CK(cudaMemcpyAsync(dOk, stepOk, (size_t)nSteps, cudaMemcpyHostToDevice, pl->st));
+    // tune failure: the reference feeds ones(F) through clip + dB (K:637-641)
+    double one = 1.0 > minAmp4Clip ? 1.0 : minAmp4Clip;
+    double failValue = 10.0 * log10(one) - gain;
+    if (isinf(failValue)) failValue = 0.0;
+    launch_scan_stitch(pl->prec, pl->rows.p, stepOk ? dOk : nullptr, dStart, dDone, nSteps, F, totalEntries, failValue, baseIsRaw,
+                       passIndex, dCur, dMx, dMn, dAv, pl->st);
+    pl->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(cur, dCur, stBytes, cudaMemcpyDeviceToHost, pl->st));
+    CK(cudaMemcpyAsync(mx, dMx, stBytes, cudaMemcpyDeviceToHost, pl->st));
+    CK(cudaMemcpyAsync(mn, dMn, stBytes, cudaMemcpyDeviceToHost, pl->st));
+    CK(cudaMemcpyAsync(av, dAv, stBytes, cudaMemcpyDeviceToHost, pl->st));
+    CK(cudaStreamSynchronize(pl->st));
+    pl->haveBatch = false;
+    return KSPEC_OK;
+}
+
+int kspec_plotcompress(kspec_plan* pl, const double* y, int64_t n, int xRes, int mode, double* out) {
+    if (check_plan(pl)) return KSPEC_ERR_ARG;
+    if (!y || !out || n < 1 || xRes < 1) { set_error("bad plotcompress arguments"); return KSPEC_ERR_ARG; }
+    if (mode < KSPEC_COMPRESS_RAW || mode > KSPEC_COMPRESS_MIN) { set_error("unknown pltCompress mode %d", mode); return KSPEC_ERR_ARG; }
+    const int64_t cols = n / xRes;
+    if (mode == KSPEC_COMPRESS_RAW || cols == 0) { memcpy(out, y, (size_t)n * 8); return KSPEC_OK; }   // K:182-183, K:191-192: identity
+    DeviceGuard guard(pl->device);
+    int rc;
+    if ((rc = pl->misc.reserve((size_t)(n + xRes) * 8))) return rc;
+    double* dY = (double*)pl->misc.p;
+    double* dO = dY + n;
+    CK(cudaMemcpyAsync(dY, y, (size_t)n * 8, cudaMemcpyHostToDevice, pl->st));
+    launch_plotcompress(dY, (int64_t)xRes * cols, xRes, mode, dO, pl->st);
+    pl->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, dO, (size_t)xRes * 8, cudaMemcpyDeviceToHost, pl->st));
+    CK(cudaStreamSynchronize(pl->st));
+    return KSPEC_OK;
+}
+
+// ---- device buffers, pinned memory, timers -----------------------------------------------------------------------
+int kspec_dev_alloc(kspec_plan* pl, int64_t bytes, void** dptr) {
+    if (check_plan(pl) || !dptr || bytes < 1) { set_error("bad argument"); return KSPEC_ERR_ARG; }
+    DeviceGuard guard(pl->device);
+    cudaError_t e = cudaMalloc(dptr, (size_t)bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc(%lld): %s", (long long)bytes, cudaGetErrorString(e)); return KSPEC_ERR_NOMEM; }
+    return KSPEC_OK;
+}
+int kspec_dev_free(kspec_plan* pl, void* dptr) {
+    if (check_plan(pl)) return KSPEC_ERR_ARG;
+    DeviceGuard guard(pl->device);
+    CK(cudaStreamSynchronize(pl->st));
+    CK(cudaFree(dptr));
+    return KSPEC_OK;
+}
+int kspec_dev_upload(kspec_plan* pl, void* dptr, const void* host, int64_t bytes) {
+    if (check_plan(pl) || !dptr || !host) { set_error("bad argument"); return KSPEC_ERR_ARG; }
+    DeviceGuard guard(pl->device);
+    CK(cudaMemcpyAsync(dptr, host, (size_t)bytes, cudaMemcpyHostToDevice, pl->st));
+    CK(cudaStreamSynchronize(pl->st));
+    return KSPEC_OK;
+}
+int kspec_dev_download(kspec_plan* pl, void* host, const void* dptr, int64_t bytes) {
+    if (check_plan(pl) || !dptr || !host) { set_error("bad argument"); return KSPEC_ERR_ARG; }
+    DeviceGuard guard(pl->device);
+    CK(cudaMemcpyAsync(host, dptr, (size_t)bytes, cudaMemcpyDeviceToHost, pl->st));
+    CK(cudaStreamSynchronize(pl->st));
+    return KSPEC_OK;
+}
+int kspec_dev_fill_l2(kspec_plan* pl) {
+    if (check_plan(pl)) return KSPEC_ERR_ARG;
+    DeviceGuard guard(pl->device);
+    const size_t bytes = (size_t)256 << 20;      // > 126 MB L2
+    int rc;
+    if ((rc = pl->l2.reserve(bytes))) return rc;
+    CK(cudaMemsetAsync(pl->l2.p, 0x5a, bytes, pl->st));
+    return KSPEC_OK;
+}
+int kspec_host_alloc(int64_t bytes, void** hptr) {
+    if (!hptr || bytes < 1) { set_error("bad argument"); return KSPEC_ERR_ARG; }
+    cudaError_t e = cudaHostAlloc(hptr, (size_t)bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaHostAlloc(%lld): %s", (long long)bytes, cudaGetErrorString(e)); return KSPEC_ERR_NOMEM; }
+    return KSPEC_OK;
+}
+int kspec_host_free(void* hptr) {
+    if (hptr) cudaFreeHost(hptr);
+    return KSPEC_OK;
+}
+int kspec_sync(kspec_plan* pl) {
+    if (check_plan(pl)) return KSPEC_ERR_ARG;
+    DeviceGuard guard(pl->device);
+    CK(cudaStreamSynchronize(pl->st));
+    return KSPEC_OK;
+}
+int kspec_timer_start(kspec_plan* pl) {
+    if (check_plan(pl)) return KSPEC_ERR_ARG;
+    DeviceGuard guard(pl->device);
+    CK(cudaEventRecord(pl->ev0, pl->st));
+    return KSPEC_OK;
+}
+int kspec_timer_stop(kspec_plan* pl, float* ms) {
+    if (check_plan(pl) || !ms) { set_error("bad argument"); return KSPEC_ERR_ARG; }
+    DeviceGuard guard(pl->device);
+    CK(cudaEventRecord(pl->ev1, pl->st));
+    CK(cudaEventSynchronize(pl->ev1));
+    CK(cudaEventElapsedTime(ms, pl->ev0, pl->ev1));
+    return KSPEC_OK;
+}
+int kspec_kernel_times(kspec_plan* pl, float* ms, int cap, int* n) {
+    if (check_plan(pl) || !ms || !n || cap < 1) { set_error("bad argument"); return KSPEC_ERR_ARG; }
+    DeviceGuard guard(pl->device);
+    CK(cudaStreamSynchronize(pl->st));
+    int64_t have = pl->kcount < kspec_plan::KT ? pl->kcount : kspec_plan::KT;
+    if (have > cap) have = cap;
+    for (int64_t i = 0; i < have; ++i) {
+        const int ks = (int)((pl->kcount - have + i) % kspec_plan::KT);
+        CK(cudaEventElapsedTime(&ms[i], pl->kev[ks][0], pl->kev[ks][1]));
+    }
+    *n = (int)have;
+    return KSPEC_OK;
+}
+int kspec_launch_count(const kspec_plan* pl, int64_t* n) {
+    if (check_plan(pl) || !n) { set_error("bad argument"); return KSPEC_ERR_ARG; }
+    *n = pl->launches;
+    return KSPEC_OK;
+}
+
+}  // extern "C"

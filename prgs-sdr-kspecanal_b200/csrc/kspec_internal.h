@@ -1,0 +1,85 @@
+// kspec_internal.h — shared declarations of libkspec.so's translation units (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <vector>
+#include "../../include/kspec.h"
+
+namespace kspec {
+
+// Arguments of the fused scan kernels (curscan_smem.cuh) and of the linear-row epilogue (epilogue.cu).
+struct ScanParams {
+    const void* samples;       // device, nScans * scanStride elements of the ingest format
+    int64_t scanStride;        // elements between consecutive scans (= fullSize)
+    int64_t nScans;
+    const int32_t* frameOffs;  // device, nFrames frame start offsets inside a scan (K:386)
+    int32_t nFrames;
+    const void* win;           // device T[F]
+    const void* tw;            // device cx<T>[F], exp(-2 pi i k / F) rounded from float64
+    int32_t cumuMode;
+    double linScale;           // 2 * winAdj / F  (K:391)
+    double u8Offset, u8Scale;
+    // per-scan epilogue
+    int32_t rowsKind;          // KSPEC_ROWS_*
+    void* rows;                // device T[nScans][F] or null
+    int32_t dbClip;            // clip to minAmp before the log (scan mode, K:640)
+    double minAmp;
+    int32_t infToZero;         // +-inf -> 0 after the log (scan mode, K:641)
+    double gain;
+    int32_t wantStats;         // emit Max/Min partials and the last avgWin dB rows
+    void* wsMax;               // device T[slots][F]
+    void* wsMin;
+    void* avgRows;             // device T[avgWin][F], row r = scan nScans-avgWin+r
+    int32_t avgWin;
+    const void* adj;           // device T[F] (shifted order) or null, subtracted for the waterfall only (K:400-411)
+    int32_t hmMode;            // KSPEC_COMPRESS_*
+    int32_t hmW;               // waterfall row width
+    void* hm;                  // device T[nScans][hmW] or null
+};
+
+struct SmemKernelInfo { int ctaThreads, smemBytes, teams, ctasPerSm; };
+
+// one per (precision, ingest format); defined in smem_inst_*.cu.  info != nullptr: query only, no launch.
+int launch_smem_f32_u8(int log2F, const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info);
+int launch_smem_f32_c64(int log2F, const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info);
+int launch_smem_f32_c128(int log2F, const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info);
+int launch_smem_f64_u8(int log2F, const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info);
+int launch_smem_f64_c64(int log2F, const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info);
+int launch_smem_f64_c128(int log2F, const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info);
+
+constexpr int SMEM_MAX_LOG2F_F32 = 14;
+constexpr int SMEM_MAX_LOG2F_F64 = 13;
+constexpr int SMEM_MIN_LOG2F = 4;
+constexpr int AVG_WINDOW = 64;   // rows that can still influence the float64 halving average (2^-63 cut-off)
+
+// ---- epilogue.cu -------------------------------------------------------------------------------------------------
+// Max/Min over the per-team partials (+ carry), Avg recurrence over the last rows (+ carry), scaled for sharding.
+void launch_stats_finish(int prec, const void* wsMax, const void* wsMin, int slots, const void* avgRows, int avgWin,
+                         int F, const double* carry /*3F or null*/, int firstIsSeed, double avgScale,
+                         double* out /*3F*/, cudaStream_t st);
+// T -> float64 widening of result rows
+void launch_widen(int prec, const void* src, double* dst, int64_t n, cudaStream_t st);
+// float64 host-side vectors -> T
+void launch_narrow(int prec, const double* src, void* dst, int64_t n, cudaStream_t st);
+// stepped-scan stitch + Max/Min/Avg (K:643-668)
+void launch_scan_stitch(int prec, const void* dbRows, const uint8_t* stepOk, const int64_t* iStart, const int64_t* iDone,
+                        int nSteps, int F, int64_t total, double failValue, int baseIsRaw, int passIndex,
+                        double* cur, double* mx, double* mn, double* av, cudaStream_t st);
+void launch_plotcompress(const double* y, int64_t n, int xRes, int mode, double* out, cudaStream_t st);
+// epilogue for engines that deliver linear, un-shifted, un-normalised |X| accumulations per scan (big FFT paths)
+void launch_linear_epilogue(int prec, const ScanParams& p, const void* acc /*T[nScans][F] natural bin order*/,
+                            int F, int slots, cudaStream_t st);
+
+// ---- bigfft.cu ---------------------------------------------------------------------------------------------------
+struct BigFft;   // four-step power-of-two engine + Bluestein wrapper
+BigFft* bigfft_create(int prec, int inFmt, int64_t F, int path, int64_t* convSize, const double* window, double u8off,
+                      double u8scale, cudaStream_t st, char* err, size_t errLen);
+void bigfft_destroy(BigFft*);
+// acc[scan][bin] (T, natural order) <- cumulate over frames of |FFT(frame * window)|
+int bigfft_run(BigFft*, const void* samples, int64_t scanStride, int64_t nScans, const int64_t* frameOffs, int nFrames,
+               int cumuMode, void* acc, int64_t* launches);
+
+void set_error(const char* fmt, ...);
+
+}  // namespace kspec

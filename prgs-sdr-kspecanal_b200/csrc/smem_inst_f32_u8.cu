@@ -1,0 +1,6 @@
+// fused scan kernels: f32 arithmetic, u8 ingest (see curscan_smem.cuh)
+#define KSPEC_INST_T float
+#define KSPEC_INST_FMT KSPEC_IN_U8_IQ
+#define KSPEC_INST_NAME launch_smem_f32_u8
+#define KSPEC_INST_MAXLOG2F 14
+#include "smem_inst.cuh"

@@ -1,0 +1,6 @@
+// fused scan kernels: f64 arithmetic, u8 ingest (see curscan_smem.cuh)
+#define KSPEC_INST_T double
+#define KSPEC_INST_FMT KSPEC_IN_U8_IQ
+#define KSPEC_INST_NAME launch_smem_f64_u8
+#define KSPEC_INST_MAXLOG2F 13
+#include "smem_inst.cuh"

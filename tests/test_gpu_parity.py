@@ -1,0 +1,288 @@
+"""GPU parity: libkspec.so (through the ctypes C ABI) against the oracle and the reference's golden vectors.
+
+Bars (BASELINE.json north_star): frame count, frame offsets, fftshift bin order and peak-bin argmax bit-exact;
+dB within 1e-3 dB of numpy float64 for bins above the clip floor (minAmp4Clip = 3.9e-8 linear).
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from kspec import _ffi, synth
+from kspec.engine import Plan
+from oracle import kspec_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DB_TOL = 1e-3            # dB, the north-star tolerance
+FS = 2.4e6
+
+
+def db(lin):
+    with np.errstate(divide="ignore"):
+        return 10 * np.log10(lin)
+
+
+def assert_db_close(got_lin, ref_lin, tol=DB_TOL, what=""):
+    """compare two linear spectra in dB on the bins above the clip floor"""
+    m = ref_lin > O.MIN_AMP4CLIP
+    err = np.abs(db(got_lin[m]) - db(ref_lin[m]))
+    assert err.size and float(err.max()) < tol, "%s max |dB err| %.3g at %d" % (what, err.max(), int(np.argmax(err)))
+    # below the floor both must be below it too
+    assert (got_lin[~m] <= O.MIN_AMP4CLIP * 1.01).all()
+
+
+def _cap(g):
+    if "capture" in g:
+        return g["capture"]
+    return g["capture_u8"]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# golden vectors produced by the unmodified reference
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,prec", [
+    ("g1_zerospan_2048_hanning.npz", "f32"), ("g1_zerospan_2048_hanning.npz", "f64"),
+    ("g1b_zerospan_1024_hamming_adj.npz", "f32"), ("g1b_zerospan_1024_hamming_adj.npz", "f64"),
+    ("g3_zerospan_8192_kaiser.npz", "f64"), ("g3_zerospan_8192_kaiser.npz", "auto"),
+])
+def test_zerospan_golden(name, prec):
+    g = load_golden(name)
+    p = g["params"]
+    F, S, n = p["fftSize"], p["fullSize"], p["nScans"]
+    cap = _cap(g)
+    with Plan(F, S, p["curScanNonOverlap"], g["window"], p["curScanCumuMode"], _ffi.in_format(cap), precision=prec) as plan:
+        assert plan.path == "smem"
+        assert np.array_equal(plan.frame_offsets(), g["offsets"])           # frame count + offsets: bit-exact
+        lin = plan.zerospan_batch(cap, n, p["gain"], p["xRes"], p["pltCompressHM"], rows="linear", want_hm=False)["rows"]
+        out = plan.zerospan_batch(cap, n, p["gain"], p["xRes"], p["pltCompressHM"], adj=g.get("adj"), rows="db")
+        one = plan.curscan(cap[:S * (2 if cap.dtype == np.uint8 else 1)])
+    tol = DB_TOL if plan.precision == "f32" else 1e-8
+    for k in range(n):
+        assert_db_close(lin[k], g["lin_rows"][k], tol, "scan %d" % k)
+        assert int(np.argmax(lin[k])) == int(np.argmax(g["lin_rows"][k]))   # peak bin: bit-exact
+    assert np.array_equal(one, lin[0])
+    assert np.max(np.abs(out["rows"] - g["db_rows"])) < tol
+    assert np.max(np.abs(out["max"] - g["fft_max"])) < tol
+    assert np.max(np.abs(out["min"] - g["fft_min"])) < tol
+    assert np.max(np.abs(out["avg"] - g["fft_avg"])) < tol
+    assert np.max(np.abs(out["hm_rows"] - g["hm"][:n])) < tol
+    assert np.array_equal(np.argmax(out["hm_rows"], axis=1), np.argmax(g["hm"][:n], axis=1))
+
+
+@pytest.mark.parametrize("name", ["g2_scan_64_r100.npz", "g2_scan_64_r050.npz", "g5a_fmscan_4096_u8.npz"])
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_scan_golden(name, prec):
+    g = load_golden(name)
+    p = g["params"]
+    F, S = p["fftSize"], p["fullSize"]
+    bufs = g["step_bufs"] if "step_bufs" in g else g["step_bufs_u8"]
+    samples = np.ascontiguousarray(bufs).reshape(-1)
+    geo = O.scan_geometry(p["startFreq"], p["endFreq"], p["samplingRate"], F, p["scanRangeNonOverlap"])
+    _, total, steps = geo
+    st = O.scan_init_state(total, p["gain"], p["minAmp4Clip"])
+    tol = DB_TOL if prec == "f32" else 1e-8
+    with Plan(F, S, p["curScanNonOverlap"], g["window"], p["curScanCumuMode"], _ffi.in_format(samples), precision=prec) as plan:
+        for ps in range(p["nPass"]):
+            ok = np.array([0 if (ps == 0 and s in p["failSteps"]) else 1 for s in range(p["nSteps"])], dtype=np.uint8)
+            plan.scan_batch(samples, p["nSteps"], [s["i_start"] for s in steps], [s["i_done"] for s in steps], total,
+                            p["minAmp4Clip"], p["gain"], st, ps, step_ok=ok, base_is_raw=p["bScanRangeBaseDataIsRaw"])
+            for k in ("cur", "max", "min", "avg"):
+                err = np.max(np.abs(st[k] - g["p%d_%s" % (ps, k)]))
+                assert err < tol, (ps, k, err)
+            hm = plan.plotcompress(st["avg"], p["xRes"], p["pltCompressHM"])
+            assert np.max(np.abs(hm - g["hm"][ps])) < tol
+    assert np.array_equal(np.argmax(st["cur"].reshape(-1, F), axis=1), np.argmax(g["p%d_cur" % (p["nPass"] - 1)].reshape(-1, F), axis=1))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# seeded oracle-vs-CUDA sweeps (sizes the oracle finishes in seconds)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("log2f", [4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14])
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_curscan_all_sizes(log2f, prec):
+    if prec == "f64" and log2f > 13:
+        pytest.skip("float64 frames above 8192 use the multi-pass engine")
+    F = 1 << log2f
+    S = O.full_size(F, FS)
+    r, wname, mode = [(0.1, "ones", "AVG"), (0.5, "hanning", "MAX"), (0.25, "hamming", "MIN"), (1.0, "hanning", "RAW")][log2f % 4]
+    win = O.window_table(wname, F)
+    x = synth.tones_noise(S, seed=100 + log2f, sigma=0.02)
+    ref = O.curscan(x.astype(np.complex128), F, r, win, mode)
+    with Plan(F, S, r, win, mode, _ffi.IN_C64, precision=prec) as plan:
+        assert np.array_equal(plan.frame_offsets(), O.frame_offsets(F, S, r))
+        got = plan.curscan(x)
+    assert_db_close(got, ref, DB_TOL if prec == "f32" else 1e-8, "F=%d" % F)
+    assert int(np.argmax(got)) == int(np.argmax(ref))
+
+
+@pytest.mark.parametrize("fmt", ["u8", "c64", "c128"])
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_ingest_formats(fmt, prec):
+    F, r = 512, 0.3
+    S = O.full_size(F, FS)
+    win = O.window_table("kaiser", F)
+    x = synth.tones_noise(S, seed=5, dtype=np.complex128, sigma=0.05)
+    if fmt == "u8":
+        raw = synth.to_u8_iq(x)
+        xin = synth.from_u8_iq(raw)
+    elif fmt == "c64":
+        raw = x.astype(np.complex64)
+        xin = raw.astype(np.complex128)
+    else:
+        raw = xin = x
+    ref = O.curscan(xin, F, r, win, "AVG")
+    with Plan(F, S, r, win, "AVG", _ffi.in_format(raw), precision=prec) as plan:
+        got = plan.curscan(raw)
+    assert_db_close(got, ref, DB_TOL if prec == "f32" else 1e-8, fmt)
+
+
+def test_u8_scale_and_offset_are_parameters():
+    """pyrtlsdr's byte->float convention is unpinned by the reference; (b-127)/128 (kspecanal.old.py:126-135) must work too."""
+    F, r = 256, 0.5
+    S = O.full_size(F, FS)
+    win = O.window_table("hanning", F)
+    raw = synth.to_u8_iq(synth.tones_noise(S, seed=9, dtype=np.complex128))
+    xin = synth.from_u8_iq(raw, offset=127.0, scale=1 / 128.0)
+    ref = O.curscan(xin, F, r, win, "AVG")
+    with Plan(F, S, r, win, "AVG", _ffi.IN_U8_IQ, precision="f64", u8_offset=127.0, u8_scale=1 / 128.0) as plan:
+        got = plan.curscan(raw)
+    assert_db_close(got, ref, 1e-8)
+
+
+@pytest.mark.parametrize("n_scans", [1, 3, 17, 64, 65, 200])
+def test_zerospan_batch_sizes_and_avg_window(n_scans):
+    """ragged batch sizes (fewer scans than teams, not a multiple of the grid) and the 64-row Avg window"""
+    F, r, gain, xres = 128, 0.5, 19.1, 32
+    S = O.full_size(F, FS)
+    win = O.window_table("hanning", F)
+    x = synth.tones_noise(n_scans * S, seed=n_scans, gate=(3000, 0.4))
+    lin = [O.curscan(x[k * S:(k + 1) * S].astype(np.complex128), F, r, win) for k in range(n_scans)]
+    ref = O.zerospan(lin, gain, xres, "AVG")
+    with Plan(F, S, r, win, "AVG", precision="f64") as plan:
+        got = plan.zerospan_batch(x, n_scans, gain, xres, "AVG", rows="db")
+    for k in ("max", "min", "avg"):
+        assert np.max(np.abs(got[k] - ref[k])) < 1e-8, k
+    assert np.max(np.abs(got["rows"] - ref["cur_rows"])) < 1e-8
+    assert np.max(np.abs(got["hm_rows"] - ref["hm_rows"])) < 1e-8
+
+
+def test_zerospan_carry_equals_one_batch():
+    """state carried across batches == one long batch == the reference loop"""
+    F, r, gain, xres = 1024, 0.1, 10.0, 256
+    S = O.full_size(F, FS)
+    win = O.window_table("hamming", F)
+    n = 12
+    x = synth.tones_noise(n * S, seed=42, gate=(20000, 0.5))
+    lin = [O.curscan(x[k * S:(k + 1) * S].astype(np.complex128), F, r, win) for k in range(n)]
+    ref = O.zerospan(lin, gain, xres, "MAX")
+    with Plan(F, S, r, win, "AVG", precision="f64") as plan:
+        a = plan.zerospan_batch(x[:5 * S], 5, gain, xres, "MAX")
+        b = plan.zerospan_batch(x[5 * S:], 7, gain, xres, "MAX", state=(a["max"], a["min"], a["avg"]))
+    for k in ("max", "min", "avg"):
+        assert np.max(np.abs(b[k] - ref[k])) < 1e-8, k
+    assert np.max(np.abs(np.vstack([a["hm_rows"], b["hm_rows"]]) - ref["hm_rows"])) < 1e-8
+
+
+@pytest.mark.parametrize("n_shards", [2, 4, 8])
+def test_sharded_partials_combine_to_the_single_gpu_result(n_shards):
+    """the multi-GPU contract on one device: MAX/MIN/SUM over per-shard partials == unsharded result"""
+    F, r, gain, xres = 256, 0.5, 19.1, 64
+    S = O.full_size(F, FS)
+    win = O.window_table("hanning", F)
+    n = 40
+    x = synth.tones_noise(n * S, seed=77, gate=(5000, 0.5))
+    with Plan(F, S, r, win, "AVG", precision="f64") as plan:
+        full = plan.zerospan_batch(x, n, gain, xres, "MAX")
+        bounds = np.linspace(0, n, n_shards + 1).astype(int)
+        parts = [plan.zerospan_batch(x[a * S:b * S], b - a, gain, xres, "MAX", scan_index_base=a, n_scans_total=n)
+                 for a, b in zip(bounds[:-1], bounds[1:])]
+    assert np.array_equal(np.max([p["max"] for p in parts], axis=0), full["max"])
+    assert np.array_equal(np.min([p["min"] for p in parts], axis=0), full["min"])
+    assert np.max(np.abs(np.sum([p["avg"] for p in parts], axis=0) - full["avg"])) < 1e-9
+    assert np.array_equal(np.vstack([p["hm_rows"] for p in parts]), full["hm_rows"])
+
+
+def test_silence_gives_minus_inf_in_zerospan_and_floor_in_scan():
+    """K:469: zeroSpan has no low clip (-inf survives); K:640-641: scan clips to minAmp4Clip"""
+    F, r = 64, 0.5
+    S = O.full_size(F, FS)
+    win = np.ones(F)
+    x = np.zeros(2 * S, dtype=np.complex64)
+    with Plan(F, S, r, win, "AVG", precision="f32") as plan:
+        z = plan.zerospan_batch(x, 2, 19.1, 64, "RAW", rows="db")
+        assert np.all(np.isneginf(z["rows"])) and np.all(np.isneginf(z["avg"]))
+        st = O.scan_init_state(2 * F, 19.1)
+        plan.scan_batch(x, 2, [0, F], [F, 2 * F], 2 * F, O.MIN_AMP4CLIP, 19.1, st, 0)
+        assert np.allclose(st["cur"], 10 * np.log10(O.MIN_AMP4CLIP) - 19.1, atol=1e-4)
+
+
+def test_scan_base_is_raw_and_quarter_overlap():
+    g = load_golden("g5b_scan_1200_cur.npz")           # geometry only; F=1200 itself needs the Bluestein engine
+    F, R, fs = 1024, 0.25, FS
+    start, end = 100e6, 100e6 + 3 * fs
+    geo = O.scan_geometry(start, end, fs, F, R)
+    _, total, steps = geo
+    S = O.full_size(F, fs)
+    win = O.window_table("hanning", F)
+    bufs = [synth.step_tones(s + 100, S) for s in range(len(steps))]
+    lin = [O.curscan(b.astype(np.complex128), F, 0.1, win) for b in bufs]
+    for raw in (False, True):
+        ref = O.scan_init_state(total, 19.1)
+        st = O.scan_init_state(total, 19.1)
+        with Plan(F, S, 0.1, win, "AVG", precision="f64") as plan:
+            for ps in range(2):
+                O.scan_pass(lin, [True] * len(steps), geo, 19.1, ref, ps, base_is_raw=raw)
+                plan.scan_batch(np.concatenate(bufs), len(steps), [s["i_start"] for s in steps], [s["i_done"] for s in steps],
+                                total, O.MIN_AMP4CLIP, 19.1, st, ps, base_is_raw=raw)
+                for k in ("cur", "max", "min", "avg"):
+                    assert np.max(np.abs(st[k] - ref[k])) < 1e-8, (raw, ps, k)
+    assert g["params"]["fftSize"] == 1200
+
+
+@pytest.mark.parametrize("mode", ["MAX", "AVG", "MIN", "RAW"])
+def test_plotcompress(mode):
+    y = np.random.default_rng(0).normal(size=36864)
+    with Plan(64, 512, 0.5, np.ones(64)) as plan:
+        got = plan.plotcompress(y, 512, mode)
+    assert np.allclose(got, O.plotcompress(y, 512, mode), rtol=0, atol=1e-12)
+
+
+def test_known_answer_tone_every_window():
+    """SURVEY section 4 KAT: bin-centred tone of amplitude A -> 2A linear (10log10(2A)-gain dB) at bin F/2+k"""
+    F, k, A = 2048, 300, 0.25
+    S = O.full_size(F, FS)
+    n = np.arange(S)
+    x = (A * np.exp(2j * np.pi * k * n / F)).astype(np.complex64)
+    for w in ("ones", "hanning", "hamming", "kaiser"):
+        win = O.window_table(w, F)
+        with Plan(F, S, 0.5, win, "AVG", precision="f32") as plan:
+            got = plan.curscan(x)
+        assert int(np.argmax(got)) == F // 2 + k
+        assert abs(got[F // 2 + k] - 2 * A) < 2e-3 * 2 * A, w
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE sizes through size-independent properties
+# ---------------------------------------------------------------------------------------------------------------
+def test_full_size_cfg1_properties():
+    """1 s capture at 2.4 MS/s (146 scans, 2190 frames), F=2048 hanning 50% overlap: sampled scans against the
+    oracle, linearity (input x2 -> +3.0103 dB), idempotence (same input twice -> identical bits)."""
+    F, r, gain, xres = 2048, 0.5, 19.1, 512
+    S = O.full_size(F, FS)
+    n = int(2.4e6) // S
+    assert n == 146
+    win = O.window_table("hanning", F)
+    x = synth.tones_noise(n * S, seed=1)
+    with Plan(F, S, r, win, "AVG", precision="f32") as plan:
+        assert plan.n_frames == 15
+        a = plan.zerospan_batch(x, n, gain, xres, "MAX", rows="db")
+        b = plan.zerospan_batch(x, n, gain, xres, "MAX", rows="db")
+        c = plan.zerospan_batch((2 * x).astype(np.complex64), n, gain, xres, "MAX", rows="db")
+    for k in ("rows", "hm_rows", "max", "min", "avg"):
+        assert np.array_equal(a[k], b[k]), k
+        assert np.max(np.abs(c[k] - a[k] - 10 * np.log10(2.0))) < 1e-4, k
+    for s in (0, 73, 145):
+        ref = O.log_nogain(O.curscan(x[s * S:(s + 1) * S].astype(np.complex128), F, r, win), gain)
+        assert np.max(np.abs(a["rows"][s] - ref)) < DB_TOL
+        assert int(np.argmax(a["rows"][s])) == int(np.argmax(ref)) == F // 2 + 256
+    assert a["hm_rows"].shape == (n, xres)
