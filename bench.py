@@ -50,36 +50,58 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region"""
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock, power and throttle reasons sampled through NVML every ~2 ms DURING the timed region
+    (an nvidia-smi subprocess is too slow for a region of a few tens of milliseconds)."""
 
     def __init__(self, gpu):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self.stop_flag = gpu, [], False
+        self.gpu, self.rows, self.stop_flag, self.err = gpu, [], False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = gpu
+            if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                idx = int(vis.split(",")[gpu])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:      # no NVML: the line says so instead of inventing numbers
+            self.nv, self.err = None, repr(e)
 
     def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.rows.append((sm, rs, pw))
+            except Exception as e:
+                self.err = repr(e)
+                return
+            time.sleep(0.002)
 
     def summary(self):
         self.stop_flag = True
-        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
-        pw = [float(r[3]) for r in self.rows if len(r) > 3 and r[3].replace(".", "").isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(self.rows), "reasons": sorted(reasons)}
+        if self.nv is None or not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "error": self.err}
+        nv = self.nv
+        sm = sorted(r[0] for r in self.rows)
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+                 "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80)}
+        reasons = sorted(k for k, bit in names.items() if any(r[1] & bit for r in self.rows))
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.max_sm, "power_w_max": max(r[2] for r in self.rows),
+                "samples": len(self.rows), "reasons": reasons}
 
 
 def base_capture():
@@ -179,7 +201,8 @@ def run_ours(args):
     from oracle import kspec_oracle as O          # cpu_baseline leg + window table only
 
     win = O.window_table("hanning", F)
-    plan = Plan(F, S, R_NONOVERLAP, win, "AVG", _ffi.IN_C64, precision="f32", device=local)
+    prec = os.environ.get("KSPEC_BENCH_PRECISION", "f32")
+    plan = Plan(F, S, R_NONOVERLAP, win, "AVG", _ffi.IN_C64, precision=prec, device=local)
     info = plan.info
     base = base_capture()
     # device-resident capture: the synthetic block tiled N_SCANS/BASE_SCANS times (content does not affect timing)
@@ -258,12 +281,12 @@ def run_ours(args):
         line = {
             "metric": "IQ Msamples/s via window+FFT+max/min/avg at fftSize 2048", "value": value, "unit": "Msamples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_all / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": plan.precision, "data": "synthetic",
             "config": {"workload": WORKLOAD, "l2": "input %.2f GiB per step >> 126 MB L2, no flush needed" % (N_SCANS * S * 8 / 2 ** 30),
                        "frames_per_s": value * 1e6 * info.n_frames / S, "parallelism": "scan-range shards x%d" % world,
                        "cta_threads": info.cta_threads, "ctas_per_sm": info.ctas_per_sm, "smem_bytes": info.smem_bytes},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                         "peak_source": peak_src, "kernel": "curscan_smem_kernel<float,C64,11>", "kernel_ms": k_ms,
+                         "peak_source": peak_src, "kernel": "curscan_smem_kernel<%s,C64,11>" % ("float" if plan.precision == "f32" else "double"), "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": algorithmic_bytes(N_SCANS)},
             "cpu_baseline": {"value": cpu_v, "unit": "Msamples/s", "cores": cores, "kind": "port", "single_core_value": cpu_1,
                              "sample": "%d scans per process x %d processes (%.0f M IQ samples), best of 2, numpy float64 oracle port" % (640, cores, 640 * cores * S / 1e6)},

@@ -43,7 +43,9 @@ typedef enum {
 enum { KSPEC_CUMU_RAW = 0, KSPEC_CUMU_AVG = 1, KSPEC_CUMU_MAX = 2, KSPEC_CUMU_MIN = 3 };
 /* IQ ingest formats: rtl_sdr raw interleaved uint8 I,Q (octave/load_rtlsdr.m:8-12), numpy complex64, numpy complex128 (K:335) */
 enum { KSPEC_IN_U8_IQ = 0, KSPEC_IN_C64 = 1, KSPEC_IN_C128 = 2 };
-/* arithmetic of the FFT/magnitude/cumulate chain.  AUTO = F32 for power-of-two fftSize <= 4096, F64 otherwise */
+/* arithmetic of the FFT/magnitude/cumulate chain.  AUTO = F64: within 1e-8 dB of the reference's float64 on every bin.
+ * F32 (power-of-two fftSize <= 16384 only) is the fast mode BASELINE.json's north_star describes: within 1e-3 dB for
+ * bins down to 1e-4 of the scan's strongest bin, absolute error ~1e-8 of that peak below (float32 rounding noise). */
 enum { KSPEC_PREC_AUTO = 0, KSPEC_PREC_F32 = 1, KSPEC_PREC_F64 = 2 };
 /* pltCompress / pltCompressHM, K:25-29, _data_plotcompress K:168-202 (MIN: documented, unreachable in the reference) */
 enum { KSPEC_COMPRESS_RAW = 0, KSPEC_COMPRESS_MAX = 1, KSPEC_COMPRESS_AVG = 2, KSPEC_COMPRESS_MIN = 3 };
@@ -65,6 +67,7 @@ typedef struct {
     int32_t ctas_per_sm;     /* smem path: resident CTAs per SM (occupancy query) */
     int32_t smem_bytes;      /* smem path: dynamic shared memory per CTA */
     int32_t scans_per_cta;   /* smem path: scans processed side by side in one CTA (tiny fftSize) */
+    int32_t tma_stages;      /* smem path: frames prefetched ahead by cp.async.bulk into shared memory (0 = direct loads) */
     int64_t conv_size;       /* Bluestein: convolution length M (power of two >= 2F-1), else 0 */
     double  win_adj;         /* F / sum(window), K:373 */
 } kspec_plan_info_t;
@@ -119,7 +122,8 @@ int kspec_scan_batch(kspec_plan* plan, const void* samples, int nSteps, const ui
 int kspec_plotcompress(kspec_plan* plan, const double* y, int64_t n, int xRes, int mode, double* out);
 
 /* ---- device-resident variants (zero-copy pipelines; what bench.py times for the roofline) ---------------------
- * kspec_dev_* manage device buffers on the plan's device; kspec_zerospan_batch_dev consumes samples already in HBM
+ * kspec_dev_* manage device buffers on the plan's device (kspec_dev_alloc adds the 16-byte tail padding the staged
+ * bulk copies need; sample buffers from other allocators must provide it themselves); kspec_zerospan_batch_dev consumes samples already in HBM
  * and leaves rows / hm rows / stats in plan-owned device buffers until kspec_zerospan_fetch copies them out.
  * kspec_timer_* bracket work on the plan's stream with CUDA events. */
 int kspec_dev_alloc(kspec_plan* plan, int64_t bytes, void** dptr);
@@ -148,6 +152,9 @@ int kspec_comm_unique_id(char id[128]);                                  /* rank
 int kspec_comm_init(kspec_comm** out, int nRanks, int rank, const char id[128], int device);
 /* MAX on max, MIN on min, SUM on avg (pre-weighted partials of kspec_zerospan_batch); n float64 each, in place */
 int kspec_comm_allreduce_stats(kspec_comm* comm, double* max, double* min, double* avg, int64_t n);
+/* same reduction directly on the statistics the plan's last kspec_zerospan_batch_dev left on the device (no host
+ * round trip; enqueued on the plan's stream, read back later with kspec_zerospan_fetch) */
+int kspec_comm_allreduce_plan(kspec_comm* comm, kspec_plan* plan);
 int kspec_comm_finalize(kspec_comm* comm);
 
 #ifdef __cplusplus

@@ -1,0 +1,261 @@
+// bigfft_kernels.cuh — float64 multi-pass engines for frames that do not fit the fused shared-memory kernel.
+//
+//   four-step   F = F1*F2 (both powers of two <= 4096): column FFTs + twiddle, then row FFTs.  cfg-4 of BASELINE.json
+//               (fftSize 2^21, "full-sample-rate window") runs here; intermediates stay L2-resident for F <= 2^22.
+//   Bluestein   any F (2.4e6 of cfg-5, 1200, odd sizes): chirp-z with a power-of-two circular convolution of length
+//               M >= 2F-1:  |X_k| = |FFT_M( conj( FFT_M(x.w.c) . V ) )_k| / M,  c_n = exp(-i pi n^2/F), V = FFT_M(conj c).
+//               The final chirp multiply has modulus one and the path only needs |X| (K:391), so it is skipped.
+//
+// Both replace the single np.fft.fft call at kspecanal.py:391; numpy itself would use mixed radix for 2.4e6.
+// The per-team register FFT is the one of fft_core.cuh; "ops" below describe where a team's elements come from and
+// where its bins go, so one kernel template serves every pass.
+#pragma once
+#include "curscan_smem.cuh"
+
+namespace kspec {
+
+typedef double2 cd;
+
+__device__ __forceinline__ cd cconj(cd a) { a.y = -a.y; return a; }
+
+// geometry shared by the pass ops: transform length M = L1*L2, element n = n1*L2 + n2, bin k = k1 + L1*k2
+struct BigGeom {
+    int64_t M;        // transform length
+    int64_t F;        // frame length (== M for four-step, < M zero padded for Bluestein)
+    int l1, l2;       // log2 L1, log2 L2
+};
+
+// ---- pass ops ---------------------------------------------------------------------------------------------------
+// Every op provides   cd load(int64_t q, int e)   and   void store(int64_t q, int k, cd v)   for batch item q.
+
+// column pass, first transform: gather the frame (fused ingest, window, optional chirp, zero padding)
+template <int INFMT> struct OpColsIn {
+    BigGeom g;
+    const void* samples; int64_t frameBase;
+    const double* win; const cd* chirp;   // chirp == nullptr for the plain four-step transform
+    const cd* twM; cd* Z;
+    double u8off, u8scale;
+    __device__ __forceinline__ cd load(int64_t q, int e) const {
+        const int64_t n = ((int64_t)e << g.l2) + q;
+        if (n >= g.F) return make_double2(0.0, 0.0);
+        cd v = Ingest<double, INFMT>::load(samples, frameBase + n, __ldg(&win[n]), u8off, u8scale);
+        if (chirp) v = cmul(v, __ldg(&chirp[n]));
+        return v;
+    }
+    __device__ __forceinline__ void store(int64_t q, int k, cd v) const {
+        Z[((int64_t)k << g.l2) + q] = cmul(v, __ldg(&twM[q * k]));
+    }
+};
+
+// column pass on a natural-order device vector (precomputing V)
+struct OpColsPlain {
+    BigGeom g; const cd* X; const cd* twM; cd* Z;
+    __device__ __forceinline__ cd load(int64_t q, int e) const { return X[((int64_t)e << g.l2) + q]; }
+    __device__ __forceinline__ void store(int64_t q, int k, cd v) const { Z[((int64_t)k << g.l2) + q] = cmul(v, __ldg(&twM[q * k])); }
+};
+
+// column pass of the SECOND Bluestein transform: its input P sits in the row pass's output layout [k1*L2 + k2]
+struct OpColsMid {
+    BigGeom g; const cd* P; const cd* twM; cd* Z;
+    __device__ __forceinline__ cd load(int64_t q, int e) const {
+        // element n = e*L2 + q of the natural-order vector lives at (n mod L1)*L2 + n div L1   (L2 >= L1)
+        const int64_t L1m = ((int64_t)1 << g.l1) - 1;
+        const int64_t loc = ((q & L1m) << g.l2) + ((int64_t)e << (g.l2 - g.l1)) + (q >> g.l1);
+        return P[loc];
+    }
+    __device__ __forceinline__ void store(int64_t q, int k, cd v) const { Z[((int64_t)k << g.l2) + q] = cmul(v, __ldg(&twM[q * k])); }
+};
+
+// row pass storing the spectrum as is, layout [k1*L2 + k2] (precomputing V)
+struct OpRowsPlain {
+    BigGeom g; const cd* Z; cd* out;
+    __device__ __forceinline__ cd load(int64_t q, int e) const { return Z[(q << g.l2) + e]; }
+    __device__ __forceinline__ void store(int64_t q, int k, cd v) const { out[(q << g.l2) + k] = v; }
+};
+
+// row pass of the first Bluestein transform: P = conj(U . V)
+struct OpRowsMul {
+    BigGeom g; const cd* Z; const cd* V; cd* P;
+    __device__ __forceinline__ cd load(int64_t q, int e) const { return Z[(q << g.l2) + e]; }
+    __device__ __forceinline__ void store(int64_t q, int k, cd v) const {
+        const int64_t i = (q << g.l2) + k;
+        P[i] = cconj(cmul(v, __ldg(&V[i])));
+    }
+};
+
+// final row pass: |X| (scaled), cumulate over frames (data_cumu, K:124-147) into acc
+struct OpRowsAcc {
+    BigGeom g; const cd* Z; double* acc; double scale; int cumuMode; int first; int transposedAcc;
+    __device__ __forceinline__ cd load(int64_t q, int e) const { return Z[(q << g.l2) + e]; }
+    __device__ __forceinline__ void store(int64_t q, int k, cd v) const {
+        const int64_t bin = q + ((int64_t)k << g.l1);
+        if (bin >= g.F) return;
+        const int64_t i = transposedAcc ? (q << g.l2) + k : bin;
+        const double mag = sqrt(v.x * v.x + v.y * v.y) * scale;
+        double a = mag;
+        if (!first) {
+            const double o = acc[i];
+            a = cumuMode == KSPEC_CUMU_AVG ? (o + mag) / 2 : cumuMode == KSPEC_CUMU_MAX ? fmax(o, mag) : cumuMode == KSPEC_CUMU_MIN ? fmin(o, mag) : mag;
+        }
+        acc[i] = a;
+    }
+};
+
+// contiguous batched transform on device vectors (V for the small Bluestein, self tests)
+struct OpPlain {
+    int l; const cd* X; cd* Y;
+    __device__ __forceinline__ cd load(int64_t q, int e) const { return X[(q << l) + e]; }
+    __device__ __forceinline__ void store(int64_t q, int k, cd v) const { Y[(q << l) + k] = v; }
+};
+
+// ---- one kernel for all passes: a team of NT threads transforms batch item q ---------------------------------------
+template <int LOG2L, typename Op>
+__global__ void __launch_bounds__(SmemCfg<double, LOG2L>::CTA, 1)
+team_fft_kernel(const Op op, const cd* __restrict__ tw, int64_t nBatch) {
+    using C = SmemCfg<double, LOG2L>;
+    constexpr int P = C::P, NT = C::NT, TEAMS = C::TEAMS, LOG2P = C::LOG2P;
+    constexpr int L0 = stage_l<LOG2L, LOG2P>(0);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int team = (TEAMS > 1) ? (threadIdx.x / NT) : 0;
+    const int tid = (TEAMS > 1) ? (threadIdx.x % NT) : threadIdx.x;
+    cd* bufA = reinterpret_cast<cd*>(smem_raw) + team * C::FPAD;
+    cd* bufB = C::DBUF ? bufA + TEAMS * C::FPAD : bufA;
+    auto sync = [] { __syncthreads(); };
+    const int64_t perIter = (int64_t)gridDim.x * TEAMS;
+    const int64_t iters = (nBatch + perIter - 1) / perIter;
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t q = it * perIter + (int64_t)blockIdx.x * TEAMS + team;
+        const bool valid = q < nBatch;
+        const int64_t qc = valid ? q : nBatch - 1;
+        cd b[P];
+#pragma unroll
+        for (int m = 0; m < P; ++m) b[m] = op.load(qc, tid + NT * m);
+        butterflies<double, P, (1 << L0), false>(b, nullptr);
+        fft_tail<double, LOG2L, LOG2P, false, C::DBUF, L0, 0, 0>(b, nullptr, tw, bufA, bufB, tid, sync);
+        if constexpr (C::DBUF && (C::NX & 1)) { cd* t = bufA; bufA = bufB; bufB = t; }
+        if (valid) {
+#pragma unroll
+            for (int m = 0; m < P; ++m) op.store(q, tid + NT * m, b[m]);
+        }
+    }
+}
+
+template <int LOG2L, typename Op>
+static int launch_team_fft(const Op& op, const cd* tw, int64_t nBatch, int smCount, cudaStream_t st) {
+    using C = SmemCfg<double, LOG2L>;
+    auto k = team_fft_kernel<LOG2L, Op>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    int64_t need = (nBatch + C::TEAMS - 1) / C::TEAMS;
+    int64_t cap = (int64_t)smCount * 4;
+    int grid = (int)(need < cap ? need : cap);
+    k<<<grid, C::CTA, C::SMEM_BYTES, st>>>(op, tw, nBatch);
+    return (int)cudaGetLastError();
+}
+
+#define KSPEC_SWITCH_L(L, LO, HI, EXPR)                       \
+    switch (L) {                                              \
+        case 4:  if constexpr (4  >= LO && 4  <= HI) { constexpr int LL = 4;  return EXPR; } break;  \
+        case 5:  if constexpr (5  >= LO && 5  <= HI) { constexpr int LL = 5;  return EXPR; } break;  \
+        case 6:  if constexpr (6  >= LO && 6  <= HI) { constexpr int LL = 6;  return EXPR; } break;  \
+        case 7:  if constexpr (7  >= LO && 7  <= HI) { constexpr int LL = 7;  return EXPR; } break;  \
+        case 8:  if constexpr (8  >= LO && 8  <= HI) { constexpr int LL = 8;  return EXPR; } break;  \
+        case 9:  if constexpr (9  >= LO && 9  <= HI) { constexpr int LL = 9;  return EXPR; } break;  \
+        case 10: if constexpr (10 >= LO && 10 <= HI) { constexpr int LL = 10; return EXPR; } break;  \
+        case 11: if constexpr (11 >= LO && 11 <= HI) { constexpr int LL = 11; return EXPR; } break;  \
+        case 12: if constexpr (12 >= LO && 12 <= HI) { constexpr int LL = 12; return EXPR; } break;  \
+        case 13: if constexpr (13 >= LO && 13 <= HI) { constexpr int LL = 13; return EXPR; } break;  \
+        default: break;                                       \
+    }
+
+// ---- Bluestein with M small enough for one team: both transforms, the product and |.| fused in one kernel -----------
+struct BlueSmallParams {
+    const void* samples; int64_t scanStride; int64_t nScans;
+    const int64_t* frameOffs; int nFrames;
+    const double* win; const cd* chirp; const cd* V; const cd* tw;
+    int F; int cumuMode; double u8off, u8scale;
+    double* acc;      // [nScans][F], natural bin order, un-normalised (the epilogue applies 2*winAdj/F)
+};
+
+template <int INFMT, int LOG2M>
+__global__ void __launch_bounds__(SmemCfg<double, LOG2M>::CTA, 1)
+bluestein_smem_kernel(const BlueSmallParams p) {
+    using C = SmemCfg<double, LOG2M>;
+    constexpr int P = C::P, NT = C::NT, TEAMS = C::TEAMS, LOG2P = C::LOG2P, M = 1 << LOG2M;
+    constexpr int L0 = stage_l<LOG2M, LOG2P>(0);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int team = (TEAMS > 1) ? (threadIdx.x / NT) : 0;
+    const int tid = (TEAMS > 1) ? (threadIdx.x % NT) : threadIdx.x;
+    cd* bufA = reinterpret_cast<cd*>(smem_raw) + team * C::FPAD;
+    cd* bufB = C::DBUF ? bufA + TEAMS * C::FPAD : bufA;
+    auto sync = [] { __syncthreads(); };
+    const int64_t perIter = (int64_t)gridDim.x * TEAMS;
+    const int64_t iters = (p.nScans + perIter - 1) / perIter;
+    const double invM = 1.0 / (double)M;
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t scan = it * perIter + (int64_t)blockIdx.x * TEAMS + team;
+        const bool valid = scan < p.nScans;
+        const int64_t sbase = (valid ? scan : p.nScans - 1) * p.scanStride;
+        double acc[P];
+        for (int f = 0; f < p.nFrames; ++f) {
+            const int64_t fbase = sbase + p.frameOffs[f];
+            cd b[P];
+#pragma unroll
+            for (int m = 0; m < P; ++m) {
+                const int n = tid + NT * m;
+                if (n < p.F) b[m] = cmul(Ingest<double, INFMT>::load(p.samples, fbase + n, __ldg(&p.win[n]), p.u8off, p.u8scale), __ldg(&p.chirp[n]));
+                else b[m] = make_double2(0.0, 0.0);
+            }
+            butterflies<double, P, (1 << L0), false>(b, nullptr);
+            fft_tail<double, LOG2M, LOG2P, false, C::DBUF, L0, 0, 0>(b, nullptr, p.tw, bufA, bufB, tid, sync);
+#pragma unroll
+            for (int m = 0; m < P; ++m) b[m] = cconj(cmul(b[m], __ldg(&p.V[tid + NT * m])));
+            butterflies<double, P, (1 << L0), false>(b, nullptr);
+            // the second transform continues the buffer alternation where the first one stopped
+            fft_tail<double, LOG2M, LOG2P, false, C::DBUF, L0, 0, C::NX>(b, nullptr, p.tw, bufA, bufB, tid, sync);
+#pragma unroll
+            for (int m = 0; m < P; ++m) {
+                const double mag = sqrt(b[m].x * b[m].x + b[m].y * b[m].y) * invM;
+                if (f == 0 || p.cumuMode == KSPEC_CUMU_RAW) acc[m] = mag;
+                else if (p.cumuMode == KSPEC_CUMU_AVG) acc[m] = (acc[m] + mag) / 2;
+                else if (p.cumuMode == KSPEC_CUMU_MAX) acc[m] = fmax(acc[m], mag);
+                else acc[m] = fmin(acc[m], mag);
+            }
+        }
+        if (valid) {
+#pragma unroll
+            for (int m = 0; m < P; ++m) {
+                const int k = tid + NT * m;
+                if (k < p.F) p.acc[scan * p.F + k] = acc[m];
+            }
+        }
+    }
+}
+
+template <int INFMT, int LOG2M>
+static int launch_bluestein_smem(const BlueSmallParams& p, int smCount, cudaStream_t st) {
+    using C = SmemCfg<double, LOG2M>;
+    auto k = bluestein_smem_kernel<INFMT, LOG2M>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    int64_t need = (p.nScans + C::TEAMS - 1) / C::TEAMS;
+    int64_t cap = (int64_t)smCount * 2;
+    int grid = (int)(need < cap ? need : cap);
+    k<<<grid, C::CTA, C::SMEM_BYTES, st>>>(p);
+    return (int)cudaGetLastError();
+}
+
+// entry points of the separately compiled instantiation units
+int big_cols_in(int inFmt, int l1, const void* op, const cd* tw, int64_t nBatch, int smCount, cudaStream_t st);
+int big_cols_plain(int l1, const OpColsPlain& op, const cd* tw, int64_t nBatch, int smCount, cudaStream_t st);
+int big_cols_mid(int l1, const OpColsMid& op, const cd* tw, int64_t nBatch, int smCount, cudaStream_t st);
+int big_rows_plain(int l2, const OpRowsPlain& op, const cd* tw, int64_t nBatch, int smCount, cudaStream_t st);
+int big_rows_mul(int l2, const OpRowsMul& op, const cd* tw, int64_t nBatch, int smCount, cudaStream_t st);
+int big_rows_acc(int l2, const OpRowsAcc& op, const cd* tw, int64_t nBatch, int smCount, cudaStream_t st);
+int big_plain(int l, const OpPlain& op, const cd* tw, int64_t nBatch, int smCount, cudaStream_t st);
+int big_blue_small(int inFmt, int logM, const BlueSmallParams& p, int smCount, cudaStream_t st);
+
+constexpr int BIG_MIN_L = 7, BIG_MAX_L = 12;      // sub-transform lengths 128..4096 -> M up to 2^24
+constexpr int BLUE_SMALL_MAX_LOGM = 13;
+
+}  // namespace kspec

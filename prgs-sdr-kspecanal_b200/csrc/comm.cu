@@ -1,8 +1,170 @@
-// comm.cu — placeholder for the NCCL stats all-reduce (next milestone).
+// comm.cu — multi-GPU exchange of the per-bin statistics: one process per GPU, captures sharded by
+// scan range, and only the Max / Min / pre-weighted Avg vectors (3 x fftSize float64, a few KB) cross NVLink:
+// one grouped NCCL all-reduce (MAX, MIN, SUM).  The reference has no counterpart (single process, K:1139-1155).
+//
+// NCCL is resolved with dlopen at first use so that libkspec.so loads on hosts without it (single-GPU use).
 #include "kspec_internal.h"
-extern "C" {
-int kspec_comm_unique_id(char*) { kspec::set_error("NCCL layer not built yet"); return KSPEC_ERR_UNSUPPORTED; }
-int kspec_comm_init(kspec_comm**, int, int, const char*, int) { kspec::set_error("NCCL layer not built yet"); return KSPEC_ERR_UNSUPPORTED; }
-int kspec_comm_allreduce_stats(kspec_comm*, double*, double*, double*, int64_t) { kspec::set_error("NCCL layer not built yet"); return KSPEC_ERR_UNSUPPORTED; }
-int kspec_comm_finalize(kspec_comm*) { return KSPEC_OK; }
+#include <dlfcn.h>
+#include <nccl.h>
+#include <string.h>
+#include <new>
+
+namespace kspec {
+
+namespace {
+
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+
+NcclApi& api() {
+    static NcclApi a;
+    if (a.h || a.ok) return a;
+    // an already loaded libnccl (e.g. the one bundled with torch) is reused: same SONAME
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+        a.h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+        if (a.h) break;
+    }
+    if (!a.h) return a;
+    a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.h, "ncclGetUniqueId");
+    a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.h, "ncclCommInitRank");
+    a.AllReduce = (decltype(a.AllReduce))dlsym(a.h, "ncclAllReduce");
+    a.GroupStart = (decltype(a.GroupStart))dlsym(a.h, "ncclGroupStart");
+    a.GroupEnd = (decltype(a.GroupEnd))dlsym(a.h, "ncclGroupEnd");
+    a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.h, "ncclCommDestroy");
+    a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.h, "ncclGetErrorString");
+    a.ok = a.GetUniqueId && a.CommInitRank && a.AllReduce && a.GroupStart && a.GroupEnd && a.CommDestroy && a.GetErrorString;
+    return a;
 }
+
+int need_api() {
+    if (!api().ok) { set_error("NCCL not available: %s", dlerror() ? dlerror() : "libnccl.so.2 could not be loaded"); return KSPEC_ERR_NCCL; }
+    return KSPEC_OK;
+}
+
+}  // namespace
+
+}  // namespace kspec
+
+using namespace kspec;
+
+struct kspec_comm {
+    ncclComm_t comm = nullptr;
+    int device = 0, nRanks = 0, rank = 0;
+    cudaStream_t st = nullptr;
+    double* buf = nullptr;
+    size_t cap = 0;
+};
+
+#define NCK(call)                                                                         \
+    do {                                                                                  \
+        ncclResult_t r_ = (call);                                                         \
+        if (r_ != ncclSuccess) {                                                          \
+            set_error("%s failed: %s", #call, api().GetErrorString(r_));                  \
+            return KSPEC_ERR_NCCL;                                                        \
+        }                                                                                 \
+    } while (0)
+#define CCK(call)                                                                         \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            set_error("%s failed: %s", #call, cudaGetErrorString(e_));                    \
+            return KSPEC_ERR_CUDA;                                                        \
+        }                                                                                 \
+    } while (0)
+
+namespace kspec {
+// grouped MAX / MIN / SUM on three consecutive device vectors of n float64 each
+int comm_allreduce_device(kspec_comm* c, double* d3n, int64_t n, cudaStream_t st) {
+    NCK(api().GroupStart());
+    NCK(api().AllReduce(d3n, d3n, (size_t)n, ncclDouble, ncclMax, c->comm, st));
+    NCK(api().AllReduce(d3n + n, d3n + n, (size_t)n, ncclDouble, ncclMin, c->comm, st));
+    NCK(api().AllReduce(d3n + 2 * n, d3n + 2 * n, (size_t)n, ncclDouble, ncclSum, c->comm, st));
+    NCK(api().GroupEnd());
+    return KSPEC_OK;
+}
+}  // namespace kspec
+
+extern "C" {
+
+int kspec_comm_unique_id(char id[128]) {
+    if (!id) { set_error("null argument"); return KSPEC_ERR_ARG; }
+    int rc = need_api();
+    if (rc) return rc;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    ncclUniqueId u;
+    NCK(api().GetUniqueId(&u));
+    memcpy(id, &u, 128);
+    return KSPEC_OK;
+}
+
+int kspec_comm_init(kspec_comm** out, int nRanks, int rank, const char id[128], int device) {
+    if (!out || !id || nRanks < 1 || rank < 0 || rank >= nRanks) { set_error("bad communicator arguments"); return KSPEC_ERR_ARG; }
+    *out = nullptr;
+    int rc = need_api();
+    if (rc) return rc;
+    CCK(cudaSetDevice(device));
+    kspec_comm* c = new (std::nothrow) kspec_comm();
+    if (!c) { set_error("out of host memory"); return KSPEC_ERR_NOMEM; }
+    c->device = device; c->nRanks = nRanks; c->rank = rank;
+    ncclUniqueId u;
+    memcpy(&u, id, 128);
+    ncclResult_t r = api().CommInitRank(&c->comm, nRanks, u, rank);
+    if (r != ncclSuccess) { set_error("ncclCommInitRank failed: %s", api().GetErrorString(r)); delete c; return KSPEC_ERR_NCCL; }
+    if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); api().CommDestroy(c->comm); delete c; return KSPEC_ERR_CUDA; }
+    *out = c;
+    return KSPEC_OK;
+}
+
+int kspec_comm_allreduce_stats(kspec_comm* c, double* mx, double* mn, double* av, int64_t n) {
+    if (!c || !mx || !mn || !av || n < 1) { set_error("bad all-reduce arguments"); return KSPEC_ERR_ARG; }
+    CCK(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)n * 8;
+    if (c->cap < 3 * bytes) {
+        if (c->buf) cudaFree(c->buf);
+        c->buf = nullptr; c->cap = 0;
+        CCK(cudaMalloc(&c->buf, 3 * bytes));
+        c->cap = 3 * bytes;
+    }
+    CCK(cudaMemcpyAsync(c->buf, mx, bytes, cudaMemcpyHostToDevice, c->st));
+    CCK(cudaMemcpyAsync(c->buf + n, mn, bytes, cudaMemcpyHostToDevice, c->st));
+    CCK(cudaMemcpyAsync(c->buf + 2 * n, av, bytes, cudaMemcpyHostToDevice, c->st));
+    int rc = comm_allreduce_device(c, c->buf, n, c->st);
+    if (rc) return rc;
+    CCK(cudaMemcpyAsync(mx, c->buf, bytes, cudaMemcpyDeviceToHost, c->st));
+    CCK(cudaMemcpyAsync(mn, c->buf + n, bytes, cudaMemcpyDeviceToHost, c->st));
+    CCK(cudaMemcpyAsync(av, c->buf + 2 * n, bytes, cudaMemcpyDeviceToHost, c->st));
+    CCK(cudaStreamSynchronize(c->st));
+    return KSPEC_OK;
+}
+
+int kspec_comm_allreduce_plan(kspec_comm* c, kspec_plan* plan) {
+    if (!c || !plan) { set_error("bad all-reduce arguments"); return KSPEC_ERR_ARG; }
+    double* stats = nullptr;
+    int F = 0;
+    cudaStream_t st = nullptr;
+    if (!plan_stats_view(plan, &stats, &F, &st)) { set_error("plan holds no batch statistics yet"); return KSPEC_ERR_STATE; }
+    CCK(cudaSetDevice(c->device));
+    return comm_allreduce_device(c, stats, F, st);
+}
+
+int kspec_comm_finalize(kspec_comm* c) {
+    if (!c) return KSPEC_OK;
+    cudaSetDevice(c->device);
+    if (c->st) cudaStreamSynchronize(c->st);
+    if (c->comm && api().ok) api().CommDestroy(c->comm);
+    if (c->buf) cudaFree(c->buf);
+    if (c->st) cudaStreamDestroy(c->st);
+    delete c;
+    return KSPEC_OK;
+}
+
+}  // extern "C"

@@ -37,23 +37,72 @@ template <typename T, int LOG2F> struct SmemCfg {
 // ---- fused IQ ingest: one sample -> cx<T>, already multiplied by the window value -----------------------------
 template <typename T, int INFMT> struct Ingest;
 template <typename T> struct Ingest<T, KSPEC_IN_U8_IQ> {
-    static __device__ __forceinline__ cx<T> load(const void* base, int64_t i, T w, T off, T scale) {
-        const uchar2 v = __ldg(reinterpret_cast<const uchar2*>(base) + i);
+    static constexpr int ELEM_BYTES = 2;
+    typedef uchar2 raw_t;
+    static __device__ __forceinline__ cx<T> conv(uchar2 v, T w, T off, T scale) {
         return mkcx<T>((((T)v.x - off) * scale) * w, (((T)v.y - off) * scale) * w);
+    }
+    static __device__ __forceinline__ cx<T> load(const void* base, int64_t i, T w, T off, T scale) {
+        return conv(__ldg(reinterpret_cast<const uchar2*>(base) + i), w, off, scale);
     }
 };
 template <typename T> struct Ingest<T, KSPEC_IN_C64> {
-    static __device__ __forceinline__ cx<T> load(const void* base, int64_t i, T w, T, T) {
-        const float2 v = __ldg(reinterpret_cast<const float2*>(base) + i);
-        return mkcx<T>((T)v.x * w, (T)v.y * w);
+    static constexpr int ELEM_BYTES = 8;
+    typedef float2 raw_t;
+    static __device__ __forceinline__ cx<T> conv(float2 v, T w, T, T) { return mkcx<T>((T)v.x * w, (T)v.y * w); }
+    static __device__ __forceinline__ cx<T> load(const void* base, int64_t i, T w, T off, T scale) {
+        return conv(__ldg(reinterpret_cast<const float2*>(base) + i), w, off, scale);
     }
 };
 template <typename T> struct Ingest<T, KSPEC_IN_C128> {
-    static __device__ __forceinline__ cx<T> load(const void* base, int64_t i, T w, T, T) {
-        const double2 v = __ldg(reinterpret_cast<const double2*>(base) + i);
-        return mkcx<T>((T)v.x * w, (T)v.y * w);
+    static constexpr int ELEM_BYTES = 16;
+    typedef double2 raw_t;
+    static __device__ __forceinline__ cx<T> conv(double2 v, T w, T, T) { return mkcx<T>((T)v.x * w, (T)v.y * w); }
+    static __device__ __forceinline__ cx<T> load(const void* base, int64_t i, T w, T off, T scale) {
+        return conv(__ldg(reinterpret_cast<const double2*>(base) + i), w, off, scale);
     }
 };
+
+// ---- TMA frame staging ----------------------------------------------------------------------------------------------
+// The raw samples of the NEXT frame(s) are fetched by one elected thread with cp.async.bulk (global -> shared,
+// completion on an mbarrier) while the CTA transforms the current frame, so the first FFT stage reads its operands
+// from shared memory and never waits on HBM/L2 latency.  A bulk copy needs 16-byte aligned addresses and sizes; frame
+// offsets int(i*F*r) (K:386) can be odd, so the copy starts at the offset rounded down to 16 bytes and carries
+// SLACK extra elements; device sample buffers therefore need 16 bytes of tail padding (kspec_dev_alloc adds it).
+template <typename T, int INFMT, int LOG2F> struct StageCfg {
+    using C = SmemCfg<T, LOG2F>;
+    static constexpr int EB = Ingest<T, INFMT>::ELEM_BYTES;
+    static constexpr int SLACK = EB >= 16 ? 0 : 16 / EB;                       // elements
+    static constexpr int STAGE_BYTES = ((C::F + SLACK) * EB + 127) / 128 * 128;
+    static constexpr int BUDGET = 225 * 1024;
+    static constexpr bool OK = C::TEAMS == 1 && C::DBUF;
+    static constexpr int STG = !OK ? 0 : (C::MINB * (C::SMEM_BYTES + 2 * STAGE_BYTES + 1024) <= BUDGET ? 2
+                                       : (C::MINB * (C::SMEM_BYTES + STAGE_BYTES + 1024) <= BUDGET ? 1 : 0));
+    static constexpr int EX_BYTES = (C::SMEM_BYTES + 127) / 128 * 128;
+    static constexpr int SMEM_BYTES = EX_BYTES + STG * STAGE_BYTES;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "KSPEC_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra KSPEC_DONE;\n\t"
+        "bra KSPEC_WAIT;\n\t"
+        "KSPEC_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 
 __device__ __forceinline__ float kabs(float2 a) {
     const float s = a.x * a.x + a.y * a.y;
@@ -74,10 +123,13 @@ template <typename T, int INFMT, int LOG2F>
 __global__ void __launch_bounds__(SmemCfg<T, LOG2F>::CTA, SmemCfg<T, LOG2F>::MINB)
 curscan_smem_kernel(const ScanParams p) {
     using C = SmemCfg<T, LOG2F>;
-    constexpr int P = C::P, F = C::F, NT = C::NT, TEAMS = C::TEAMS, LOG2P = C::LOG2P;
+    using SC = StageCfg<T, INFMT, LOG2F>;
+    using IN = Ingest<T, INFMT>;
+    constexpr int P = C::P, F = C::F, NT = C::NT, TEAMS = C::TEAMS, LOG2P = C::LOG2P, STG = SC::STG;
     constexpr int L0 = stage_l<LOG2F, LOG2P>(0);
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t mbar[2];
     const int team = (TEAMS > 1) ? (threadIdx.x / NT) : 0;
     const int tid = (TEAMS > 1) ? (threadIdx.x % NT) : threadIdx.x;
     // two exchange buffers per team (bufA/bufB) when they fit, else one.  Exchange x of a frame uses bufA for even
@@ -85,6 +137,7 @@ curscan_smem_kernel(const ScanParams p) {
     // rewritten before a full barrier separates it from its last readers.
     cx<T>* bufA = reinterpret_cast<cx<T>*>(smem_raw) + team * C::FPAD;
     cx<T>* bufB = C::DBUF ? bufA + TEAMS * C::FPAD : bufA;
+    unsigned char* stage0 = smem_raw + SC::EX_BYTES;
 
     const T* __restrict__ gwin = reinterpret_cast<const T*>(p.win);
     const cx<T>* __restrict__ gtw = reinterpret_cast<const cx<T>*>(p.tw);
@@ -105,6 +158,34 @@ curscan_smem_kernel(const ScanParams p) {
     const int64_t scansPerIter = (int64_t)gridDim.x * TEAMS;
     const int64_t iters = (p.nScans + scansPerIter - 1) / scansPerIter;
 
+    // ---- staged pipeline bookkeeping (one elected thread issues the bulk copies) ---------------------------------------
+    const int64_t totalFrames = iters * p.nFrames;          // frames this CTA walks through, g = it*nFrames + f
+    auto issue = [&](int64_t g) {
+        // called by thread 0 only: fetch frame g into stage buffer g % STG
+        const int64_t it = g / p.nFrames;
+        const int f = (int)(g - it * p.nFrames);
+        int64_t sc = it * scansPerIter + slot;
+        if (sc >= p.nScans) sc = p.nScans - 1;
+        const int64_t e0 = sc * p.scanStride + p.frameOffs[f];
+        const int64_t e0a = (SC::SLACK > 0) ? (e0 & ~(int64_t)(SC::SLACK - 1)) : e0;
+        const int s = (STG == 2) ? (int)(g & 1) : 0;
+        constexpr uint32_t bytes = (uint32_t)((F + SC::SLACK) * SC::EB);
+        mbar_expect_tx(&mbar[s], bytes);
+        tma_load_1d(stage0 + s * SC::STAGE_BYTES, reinterpret_cast<const unsigned char*>(p.samples) + e0a * SC::EB, bytes, &mbar[s]);
+    };
+    if constexpr (STG > 0) {
+        if (threadIdx.x == 0) {
+            mbar_init(&mbar[0], 1);
+            mbar_init(&mbar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int g = 0; g < STG && g < totalFrames; ++g) issue(g);
+        }
+    }
+
+    int64_t g = 0;
     for (int64_t it = 0; it < iters; ++it) {
         const int64_t scan = it * scansPerIter + slot;
         const bool valid = scan < p.nScans;
@@ -112,16 +193,38 @@ curscan_smem_kernel(const ScanParams p) {
         const int64_t sbase = scanC * p.scanStride;
 
         T acc[P];
-        for (int f = 0; f < p.nFrames; ++f) {
+        for (int f = 0; f < p.nFrames; ++f, ++g) {
             const int64_t fbase = sbase + p.frameOffs[f];
             cx<T> b[P];
+            if constexpr (STG > 0) {
+                const int s = (STG == 2) ? (int)(g & 1) : 0;
+                const uint32_t parity = (STG == 2) ? (uint32_t)((g >> 1) & 1) : (uint32_t)(g & 1);
+                mbar_wait(&mbar[s], parity);
+                const typename IN::raw_t* sp = reinterpret_cast<const typename IN::raw_t*>(stage0 + s * SC::STAGE_BYTES) +
+                                               (SC::SLACK > 0 ? (int)(fbase & (SC::SLACK - 1)) : 0);
 #pragma unroll
-            for (int m = 0; m < P; ++m) {
-                const T w = C::REGTAB ? win[m] : __ldg(&gwin[tid + NT * m]);
-                b[m] = Ingest<T, INFMT>::load(p.samples, fbase + tid + NT * m, w, u8off, u8scale);
+                for (int m = 0; m < P; ++m) {
+                    const T w = C::REGTAB ? win[m] : __ldg(&gwin[tid + NT * m]);
+                    b[m] = IN::conv(sp[tid + NT * m], w, u8off, u8scale);
+                }
+            } else {
+#pragma unroll
+                for (int m = 0; m < P; ++m) {
+                    const T w = C::REGTAB ? win[m] : __ldg(&gwin[tid + NT * m]);
+                    b[m] = IN::load(p.samples, fbase + tid + NT * m, w, u8off, u8scale);
+                }
             }
             butterflies<T, P, (1 << L0), false>(b, nullptr);
-            fft_tail<T, LOG2F, LOG2P, C::REGTAB, C::DBUF, L0, 0, 0>(b, twl, gtw, bufA, bufB, tid, sync);
+            if constexpr (STG > 0) {
+                // the first exchange's barrier also tells thread 0 that every thread has consumed the stage buffer
+                auto sync_and_refill = [&] {
+                    __syncthreads();
+                    if (threadIdx.x == 0 && g + STG < totalFrames) issue(g + STG);
+                };
+                fft_tail_first<T, LOG2F, LOG2P, C::REGTAB, C::DBUF, L0>(b, twl, gtw, bufA, bufB, tid, sync, sync_and_refill);
+            } else {
+                fft_tail<T, LOG2F, LOG2P, C::REGTAB, C::DBUF, L0, 0, 0>(b, twl, gtw, bufA, bufB, tid, sync);
+            }
             if constexpr (C::DBUF && (C::NX & 1)) { cx<T>* t = bufA; bufA = bufB; bufB = t; }
             // |X| and cumulate over the frames of this scan (data_cumu, K:124-147); normalisation is applied once per scan
             if (f == 0 || p.cumuMode == KSPEC_CUMU_RAW) {
@@ -175,18 +278,18 @@ curscan_smem_kernel(const ScanParams p) {
         if (needRow) {
             __syncthreads();
             // _data_plotcompress (K:184-200): W groups of g adjacent bins
-            const int W = p.hmW, g = F / W;
+            const int W = p.hmW, gsz = F / W;
             T* __restrict__ hm = reinterpret_cast<T*>(p.hm);
             const T* row = erow;
             for (int w = tid; w < W; w += NT) {
-                T r = row[w * g];
+                T r = row[w * gsz];
                 if (p.hmMode == KSPEC_COMPRESS_MAX) {
-                    for (int q = 1; q < g; ++q) r = fmax(r, row[w * g + q]);
+                    for (int q = 1; q < gsz; ++q) r = fmax(r, row[w * gsz + q]);
                 } else if (p.hmMode == KSPEC_COMPRESS_MIN) {
-                    for (int q = 1; q < g; ++q) r = fmin(r, row[w * g + q]);
+                    for (int q = 1; q < gsz; ++q) r = fmin(r, row[w * gsz + q]);
                 } else if (p.hmMode == KSPEC_COMPRESS_AVG) {
-                    for (int q = 1; q < g; ++q) r += row[w * g + q];
-                    r /= (T)g;
+                    for (int q = 1; q < gsz; ++q) r += row[w * gsz + q];
+                    r /= (T)gsz;
                 }
                 if (valid) hm[scan * W + w] = r;
             }
@@ -198,25 +301,21 @@ curscan_smem_kernel(const ScanParams p) {
 template <typename T, int INFMT, int LOG2F>
 static int launch_smem_one(const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info) {
     using C = SmemCfg<T, LOG2F>;
+    using SC = StageCfg<T, INFMT, LOG2F>;
     auto k = curscan_smem_kernel<T, INFMT, LOG2F>;
-    static bool attr_done[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!attr_done[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-        if (e != cudaSuccess) return (int)e;
-        attr_done[dev & 63] = true;
-    }
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SC::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
     if (info) {
         info->ctaThreads = C::CTA;
-        info->smemBytes = C::SMEM_BYTES;
+        info->smemBytes = SC::SMEM_BYTES;
         info->teams = C::TEAMS;
+        info->stages = SC::STG;
         int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, C::CTA, C::SMEM_BYTES);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, C::CTA, SC::SMEM_BYTES);
         info->ctasPerSm = nb;
         return 0;
     }
-    k<<<grid, C::CTA, C::SMEM_BYTES, st>>>(p);
+    k<<<grid, C::CTA, SC::SMEM_BYTES, st>>>(p);
     return (int)cudaGetLastError();
 }
 

@@ -113,7 +113,8 @@ __global__ void linear_epilogue_kernel(const ScanParams p, const T* __restrict__
     if (j >= F) return;
     // np.fft.fftshift (K:396) rolls by F//2:  out = concat(in[ceil(F/2):], in[:ceil(F/2)])  ->  out[j] = in[(j + ceil(F/2)) mod F]
     const int c2 = (F + 1) / 2;
-    const int src = (j + c2) % F;
+    const int srcBin = (j + c2) % F;
+    const int src = p.accL1 ? (((srcBin & ((1 << p.accL1) - 1)) << p.accL2) + (srcBin >> p.accL1)) : srcBin;
     T* rows = reinterpret_cast<T*>(p.rows);
     T mx = 0, mn = 0;
     for (int64_t s = 0; s < p.nScans; ++s) {
@@ -151,7 +152,9 @@ __global__ void linear_hm_kernel(const ScanParams p, const T* __restrict__ acc, 
     T r = (mode == KSPEC_COMPRESS_MAX) ? -inf : (mode == KSPEC_COMPRESS_MIN ? inf : (T)0);
     for (int q = threadIdx.x; q < g; q += blockDim.x) {
         const int j = w * g + q;
-        T lin = acc[s * F + (j + c2) % F] * (T)p.linScale;
+        const int srcBin = (j + c2) % F;
+        const int src = p.accL1 ? (((srcBin & ((1 << p.accL1) - 1)) << p.accL2) + (srcBin >> p.accL1)) : srcBin;
+        T lin = acc[s * F + src] * (T)p.linScale;
         if (p.dbClip) lin = fmax(lin, (T)p.minAmp);
         T db = db_of(lin) - (T)p.gain;
         if (p.infToZero && isinf(db)) db = (T)0;

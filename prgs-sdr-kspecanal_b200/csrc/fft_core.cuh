@@ -218,4 +218,31 @@ __device__ __forceinline__ void fft_tail(cx<T> (&b)[1 << LOG2P], const cx<T>* tw
     }
 }
 
+// Same as fft_tail, but the barrier of the FIRST exchange is `syncFirst` (the staged kernel re-arms its TMA prefetch
+// there: once every thread is past that barrier the stage buffer has been fully consumed).
+template <typename T, int LOG2F, int LOG2P, bool TWREGS, bool DBUF, int LNS, typename Sync, typename SyncFirst>
+__device__ __forceinline__ void fft_tail_first(cx<T> (&b)[1 << LOG2P], const cx<T>* twl, const cx<T>* __restrict__ table,
+                                               cx<T>* buf0, cx<T>* buf1, int tid, Sync sync, SyncFirst syncFirst) {
+    static_assert(LNS < LOG2F, "needs at least one exchange");
+    constexpr int P = 1 << LOG2P, F = 1 << LOG2F, NT = F / P;
+    constexpr int L = stage_l<LOG2F, LOG2P>(LNS), R = 1 << L, V = P / R;
+    if constexpr (!DBUF) sync();
+    scatter<T, P, (1 << LOG2P), NT, LNS - LOG2P>(b, buf0, tid);
+    syncFirst();
+    gather<T, P, NT>(b, buf0, tid);
+    if constexpr (TWREGS) {
+        butterflies<T, P, R, true>(b, twl);
+    } else {
+        cx<T> tw[V * (R - 1)];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const int k = (tid + v * NT) & ((1 << LNS) - 1);
+#pragma unroll
+            for (int t = 1; t < R; ++t) tw[v * (R - 1) + (t - 1)] = __ldg(&table[(t * k) << (LOG2F - LNS - L)]);
+        }
+        butterflies<T, P, R, true>(b, tw);
+    }
+    fft_tail<T, LOG2F, LOG2P, TWREGS, DBUF, LNS + L, V * (R - 1), 1>(b, twl, table, buf0, buf1, tid, sync);
+}
+
 }  // namespace kspec

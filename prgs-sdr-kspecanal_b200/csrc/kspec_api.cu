@@ -85,6 +85,7 @@ struct kspec_plan {
 
 namespace {
 
+constexpr size_t TAIL_PAD = 64;   // bytes a staged bulk copy may read past the last frame (rounded to 16 B)
 size_t in_elem_bytes(int fmt) { return fmt == KSPEC_IN_U8_IQ ? 2 : (fmt == KSPEC_IN_C64 ? 8 : 16); }
 size_t real_bytes(int prec) { return prec == KSPEC_PREC_F32 ? 4 : 8; }
 
@@ -158,6 +159,8 @@ int run_engine(kspec_plan* pl, ScanParams& p, int* slotsOut) {
     }
     rc = bigfft_run(pl->big, p.samples, pl->S, p.nScans, pl->offs.data(), (int)pl->offs.size(), pl->cumu, pl->acc.p, &pl->launches);
     if (rc) return rc;
+    p.accL1 = bigfft_acc_l1(pl->big);
+    p.accL2 = bigfft_acc_l2(pl->big);
     launch_linear_epilogue(pl->prec, p, pl->acc.p, pl->F, 1, pl->st);
     pl->launches += p.hm ? 2 : 1;
     *slotsOut = 1;
@@ -172,6 +175,16 @@ int check_plan(const kspec_plan* pl) {
 int hm_width(int F, int xRes, int hmMode) { return (hmMode != KSPEC_COMPRESS_RAW && F > xRes) ? xRes : F; }
 
 }  // namespace
+
+namespace kspec {
+bool plan_stats_view(kspec_plan* pl, double** stats3F, int* F, cudaStream_t* st) {
+    if (!pl || !pl->haveBatch || !pl->stats.p) return false;
+    *stats3F = (double*)pl->stats.p;
+    *F = pl->F;
+    *st = pl->st;
+    return true;
+}
+}  // namespace kspec
 
 extern "C" {
 
@@ -210,7 +223,7 @@ int kspec_plan_create(kspec_plan** out, int fftSize, int64_t fullSize, double no
     pl->u8off = u8_offset; pl->u8scale = u8_scale;
     const bool pow2 = (fftSize & (fftSize - 1)) == 0;
     if (pow2) { int l = 0; while ((1 << l) < fftSize) ++l; pl->log2F = l; }
-    if (precision == KSPEC_PREC_AUTO) precision = (pow2 && fftSize <= 4096) ? KSPEC_PREC_F32 : KSPEC_PREC_F64;
+    if (precision == KSPEC_PREC_AUTO) precision = KSPEC_PREC_F64;     // parity first; F32 is the explicit fast mode
     pl->prec = precision;
     const int smemMax = precision == KSPEC_PREC_F32 ? SMEM_MAX_LOG2F_F32 : SMEM_MAX_LOG2F_F64;
     if (pow2 && pl->log2F >= SMEM_MIN_LOG2F && pl->log2F <= smemMax) pl->path = KSPEC_PATH_SMEM;
@@ -322,7 +335,7 @@ int kspec_plan_info(const kspec_plan* pl, kspec_plan_info_t* info) {
     info->fft_size = pl->F; info->full_size = pl->S; info->n_frames = (int)pl->offs.size(); info->precision = pl->prec;
     info->path = pl->path; info->in_fmt = pl->inFmt; info->device = pl->device; info->sm_count = pl->smCount;
     info->cta_threads = pl->ki.ctaThreads; info->ctas_per_sm = pl->ki.ctasPerSm; info->smem_bytes = pl->ki.smemBytes;
-    info->scans_per_cta = pl->ki.teams; info->conv_size = pl->convSize; info->win_adj = pl->winAdj;
+    info->scans_per_cta = pl->ki.teams; info->tma_stages = pl->ki.stages; info->conv_size = pl->convSize; info->win_adj = pl->winAdj;
     return KSPEC_OK;
 }
 
@@ -425,7 +438,7 @@ int kspec_zerospan_batch(kspec_plan* pl, const void* samples, int64_t nScans, do
     DeviceGuard guard(pl->device);
     const size_t bytes = (size_t)nScans * pl->S * in_elem_bytes(pl->inFmt);
     int rc;
-    if ((rc = pl->in.reserve(bytes))) return rc;
+    if ((rc = pl->in.reserve(bytes + TAIL_PAD))) return rc;
     CK(cudaMemcpyAsync(pl->in.p, samples, bytes, cudaMemcpyHostToDevice, pl->st));
     if ((rc = kspec_zerospan_batch_dev(pl, pl->in.p, nScans, gain, adj, hmMode, xRes, rowsKind, hm_rows != nullptr, mx, mn, av, carry,
                                        scanIndexBase, nScansTotal)))
@@ -441,7 +454,7 @@ int kspec_curscan(kspec_plan* pl, const void* samples, double* out) {
     const size_t rb = real_bytes(pl->prec);
     const size_t bytes = (size_t)pl->S * in_elem_bytes(pl->inFmt);
     int rc;
-    if ((rc = pl->in.reserve(bytes)) || (rc = pl->rows.reserve((size_t)F * rb))) return rc;
+    if ((rc = pl->in.reserve(bytes + TAIL_PAD)) || (rc = pl->rows.reserve((size_t)F * rb))) return rc;
     CK(cudaMemcpyAsync(pl->in.p, samples, bytes, cudaMemcpyHostToDevice, pl->st));
     ScanParams p = base_params(pl, pl->in.p, 1);
     p.rowsKind = KSPEC_ROWS_LINEAR;
@@ -473,7 +486,7 @@ int kspec_scan_batch(kspec_plan* pl, const void* samples, int nSteps, const uint
     const size_t rb = real_bytes(pl->prec);
     const size_t bytes = (size_t)nSteps * pl->S * in_elem_bytes(pl->inFmt);
     int rc;
-    if ((rc = pl->in.reserve(bytes)) || (rc = pl->rows.reserve((size_t)nSteps * F * rb))) return rc;
+    if ((rc = pl->in.reserve(bytes + TAIL_PAD)) || (rc = pl->rows.reserve((size_t)nSteps * F * rb))) return rc;
     CK(cudaMemcpyAsync(pl->in.p, samples, bytes, cudaMemcpyHostToDevice, pl->st));
     ScanParams p = base_params(pl, pl->in.p, nSteps);
     p.rowsKind = KSPEC_ROWS_DB;
@@ -539,7 +552,7 @@ int kspec_plotcompress(kspec_plan* pl, const double* y, int64_t n, int xRes, int
 int kspec_dev_alloc(kspec_plan* pl, int64_t bytes, void** dptr) {
     if (check_plan(pl) || !dptr || bytes < 1) { set_error("bad argument"); return KSPEC_ERR_ARG; }
     DeviceGuard guard(pl->device);
-    cudaError_t e = cudaMalloc(dptr, (size_t)bytes);
+    cudaError_t e = cudaMalloc(dptr, (size_t)bytes + TAIL_PAD);     // tail padding: see StageCfg (16-byte granular bulk copies)
     if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc(%lld): %s", (long long)bytes, cudaGetErrorString(e)); return KSPEC_ERR_NOMEM; }
     return KSPEC_OK;
 }

@@ -36,9 +36,11 @@ struct ScanParams {
     int32_t hmMode;            // KSPEC_COMPRESS_*
     int32_t hmW;               // waterfall row width
     void* hm;                  // device T[nScans][hmW] or null
+    // linear-row engines only: accumulation rows stored [k1][k2] with bin k = k1 + 2^accL1 * k2 (0: natural order)
+    int32_t accL1, accL2;
 };
 
-struct SmemKernelInfo { int ctaThreads, smemBytes, teams, ctasPerSm; };
+struct SmemKernelInfo { int ctaThreads, smemBytes, teams, ctasPerSm, stages; };
 
 // one per (precision, ingest format); defined in smem_inst_*.cu.  info != nullptr: query only, no launch.
 int launch_smem_f32_u8(int log2F, const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info);
@@ -80,6 +82,12 @@ void bigfft_destroy(BigFft*);
 int bigfft_run(BigFft*, const void* samples, int64_t scanStride, int64_t nScans, const int64_t* frameOffs, int nFrames,
                int cumuMode, void* acc, int64_t* launches);
 
+int bigfft_acc_l1(const BigFft*);
+int bigfft_acc_l2(const BigFft*);
+
 void set_error(const char* fmt, ...);
+
+// comm.cu <- kspec_api.cu: device view of the [max | min | avg] vectors the last zeroSpan batch left in the plan
+bool plan_stats_view(kspec_plan* plan, double** stats3F, int* F, cudaStream_t* st);
 
 }  // namespace kspec

@@ -32,6 +32,7 @@ class PlanInfo(C.Structure):
         ("fft_size", C.c_int32), ("full_size", C.c_int64), ("n_frames", C.c_int32), ("precision", C.c_int32),
         ("path", C.c_int32), ("in_fmt", C.c_int32), ("device", C.c_int32), ("sm_count", C.c_int32),
         ("cta_threads", C.c_int32), ("ctas_per_sm", C.c_int32), ("smem_bytes", C.c_int32), ("scans_per_cta", C.c_int32),
+        ("tma_stages", C.c_int32),
         ("conv_size", C.c_int64), ("win_adj", C.c_double),
     ]
 
@@ -73,6 +74,7 @@ SIGNATURES = {
     "kspec_comm_unique_id": (C.c_int, [C.c_char_p]),
     "kspec_comm_init": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_char_p, C.c_int]),
     "kspec_comm_allreduce_stats": (C.c_int, [_P, _D, _D, _D, _I64]),
+    "kspec_comm_allreduce_plan": (C.c_int, [_P, _P]),
     "kspec_comm_finalize": (C.c_int, [_P]),
 }
 

@@ -1,0 +1,49 @@
+"""Multi-GPU exchange of the per-bin statistics (one process per GPU, NCCL over NVLink/NVSwitch).
+
+Captures are sharded by scan range (``kspec.sharding``); every rank runs its shard with
+``Plan.zerospan_batch(..., scan_index_base=a, n_scans_total=n)`` and then calls ``allreduce_*`` once:
+MAX on Fft.Max, MIN on Fft.Min, SUM on the pre-weighted Fft.Avg partials.  Waterfall / Cur rows stay on the rank
+that produced them.  The reference has no counterpart (it is a single process, kspecanal.py:1139-1155).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import check, dptr
+
+
+class Comm:
+    @staticmethod
+    def unique_id():
+        """128-byte NCCL id; rank 0 creates it and ships it to the other ranks (any out-of-band channel)."""
+        buf = C.create_string_buffer(128)
+        check(_ffi.lib().kspec_comm_unique_id(buf))
+        return buf.raw
+
+    def __init__(self, n_ranks, rank, uid, device):
+        self._h = C.c_void_p()
+        assert len(uid) == 128
+        check(_ffi.lib().kspec_comm_init(C.byref(self._h), int(n_ranks), int(rank), C.create_string_buffer(uid, 128), int(device)))
+        self.n_ranks, self.rank = n_ranks, rank
+
+    def allreduce_host(self, mx, mn, av):
+        """in place on float64 host vectors"""
+        for a in (mx, mn, av):
+            assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+        check(_ffi.lib().kspec_comm_allreduce_stats(self._h, dptr(mx), dptr(mn), dptr(av), len(mx)))
+
+    def allreduce_plan_stats(self, plan):
+        """in place on the statistics plan.zerospan_batch_dev left on the device (stream ordered, no host copy)"""
+        check(_ffi.lib().kspec_comm_allreduce_plan(self._h, plan._h))
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            _ffi.lib().kspec_comm_finalize(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,33 @@
+"""Scan-range / step-range sharding arithmetic for multi-GPU runs.  Pure host integer logic, no GPU.
+
+zeroSpan: the unit is one scan (fullSize contiguous samples, K:370); overlap exists only inside a scan, so shards
+need no halo.  Each rank gets a contiguous range; Max/Min combine with MAX/MIN, Avg partials are pre-weighted with
+the global halving weights (data_cumu AVG, K:137-139) so that a plain SUM reproduces the sequential recurrence.
+"""
+import numpy as np
+
+
+def shard_bounds(n_units, n_ranks):
+    """contiguous [a, b) per rank, sizes differ by at most one, earlier ranks get the larger shards"""
+    base, extra = divmod(int(n_units), int(n_ranks))
+    out, a = [], 0
+    for r in range(n_ranks):
+        b = a + base + (1 if r < extra else 0)
+        out.append((a, b))
+        a = b
+    return out
+
+
+def avg_weights(n_total):
+    """weights w_k of the halving recurrence A_0 = x_0, A_k = (A_{k-1} + x_k)/2 after n_total items (float64)"""
+    k = np.arange(n_total)
+    w = np.ldexp(1.0, -(n_total - k).astype(np.int64))
+    if n_total:
+        w[0] = np.ldexp(1.0, -(n_total - 1))
+    return w
+
+
+def combine_stats(parts):
+    """host-side equivalent of kspec_comm_allreduce_stats over a list of per-shard dicts (max, min, avg partial)"""
+    return dict(max=np.max([p["max"] for p in parts], axis=0), min=np.min([p["min"] for p in parts], axis=0),
+                avg=np.sum([p["avg"] for p in parts], axis=0))

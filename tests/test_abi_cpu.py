@@ -35,8 +35,8 @@ def test_library_exports_every_symbol():
 
 
 def test_plan_info_struct_matches_header():
-    # 4 (+4 pad) + 8 + 10*4 + 8 + 8 with natural alignment
-    assert ctypes.sizeof(_ffi.PlanInfo) == 72
+    # 4 (+4 pad) + 8 + 11*4 (+4 pad) + 8 + 8 with natural alignment
+    assert ctypes.sizeof(_ffi.PlanInfo) == 80
 
 
 @pytest.mark.skipif(device_count() > 0, reason="only meaningful without a GPU")
