@@ -18,18 +18,21 @@
 
 namespace kspec {
 
-template <typename T, int LOG2F> struct SmemCfg {
+// VAR selects a tuning variant of the same kernel (A/B experiments, see profiles/README.md):
+//   0 production   1 twiddles via L1 instead of registers, 4 CTAs/SM   2 as 1 without TMA staging   3 as 0 with one stage
+template <typename T, int LOG2F, int VAR = 0> struct SmemCfg {
     static constexpr int LOG2P = LOG2F >= 7 ? 4 : (LOG2F >= 5 ? 3 : 2);
     static constexpr int P = 1 << LOG2P, F = 1 << LOG2F, NT = F / P;
     static constexpr int CTA = NT < 128 ? 128 : NT;
     static constexpr int TEAMS = CTA / NT;
     static constexpr bool F32 = sizeof(T) == 4;
-    static constexpr bool REGTAB = F32 && LOG2F <= 11;   // window + twiddles live in registers across frames
+    static constexpr bool REGTAB = F32 && LOG2F <= 11;   // window (and, by default, twiddles) live in registers across frames
+    static constexpr bool TWREG = REGTAB && !(VAR == 1 || VAR == 2);
     static constexpr int FPAD = padded_len(F);
     static constexpr int BUF_BYTES = FPAD * (int)sizeof(cx<T>) * TEAMS;
     static constexpr bool DBUF = 2 * BUF_BYTES <= 160 * 1024;
     static constexpr int SMEM_BYTES = (DBUF ? 2 : 1) * BUF_BYTES;
-    static constexpr int MINB = CTA == 128 ? (F32 ? 3 : 2) : (CTA == 256 ? (F32 ? 2 : 1) : 1);
+    static constexpr int MINB = (VAR == 1 || VAR == 2) ? 4 : (CTA == 128 ? (F32 ? 3 : 2) : (CTA == 256 ? (F32 ? 2 : 1) : 1));
     static constexpr int NTW = twiddle_count<LOG2F, LOG2P>();
     static constexpr int NX = exchange_count<LOG2F, LOG2P>();
 };
@@ -69,15 +72,16 @@ template <typename T> struct Ingest<T, KSPEC_IN_C128> {
 // from shared memory and never waits on HBM/L2 latency.  A bulk copy needs 16-byte aligned addresses and sizes; frame
 // offsets int(i*F*r) (K:386) can be odd, so the copy starts at the offset rounded down to 16 bytes and carries
 // SLACK extra elements; device sample buffers therefore need 16 bytes of tail padding (kspec_dev_alloc adds it).
-template <typename T, int INFMT, int LOG2F> struct StageCfg {
-    using C = SmemCfg<T, LOG2F>;
+template <typename T, int INFMT, int LOG2F, int VAR = 0> struct StageCfg {
+    using C = SmemCfg<T, LOG2F, VAR>;
     static constexpr int EB = Ingest<T, INFMT>::ELEM_BYTES;
     static constexpr int SLACK = EB >= 16 ? 0 : 16 / EB;                       // elements
     static constexpr int STAGE_BYTES = ((C::F + SLACK) * EB + 127) / 128 * 128;
     static constexpr int BUDGET = 225 * 1024;
     static constexpr bool OK = C::TEAMS == 1 && C::DBUF;
-    static constexpr int STG = !OK ? 0 : (C::MINB * (C::SMEM_BYTES + 2 * STAGE_BYTES + 1024) <= BUDGET ? 2
-                                       : (C::MINB * (C::SMEM_BYTES + STAGE_BYTES + 1024) <= BUDGET ? 1 : 0));
+    static constexpr int STG_AUTO = !OK ? 0 : (C::MINB * (C::SMEM_BYTES + 2 * STAGE_BYTES + 1024) <= BUDGET ? 2
+                                            : (C::MINB * (C::SMEM_BYTES + STAGE_BYTES + 1024) <= BUDGET ? 1 : 0));
+    static constexpr int STG = VAR == 2 ? 0 : (VAR == 3 ? (STG_AUTO > 1 ? 1 : STG_AUTO) : STG_AUTO);
     static constexpr int EX_BYTES = (C::SMEM_BYTES + 127) / 128 * 128;
     static constexpr int SMEM_BYTES = EX_BYTES + STG * STAGE_BYTES;
 };
@@ -119,11 +123,11 @@ template <typename T> __device__ __forceinline__ T pos_inf();
 template <> __device__ __forceinline__ float pos_inf<float>() { return __int_as_float(0x7f800000); }
 template <> __device__ __forceinline__ double pos_inf<double>() { return __longlong_as_double(0x7ff0000000000000LL); }
 
-template <typename T, int INFMT, int LOG2F>
-__global__ void __launch_bounds__(SmemCfg<T, LOG2F>::CTA, SmemCfg<T, LOG2F>::MINB)
+template <typename T, int INFMT, int LOG2F, int VAR = 0>
+__global__ void __launch_bounds__(SmemCfg<T, LOG2F, VAR>::CTA, SmemCfg<T, LOG2F, VAR>::MINB)
 curscan_smem_kernel(const ScanParams p) {
-    using C = SmemCfg<T, LOG2F>;
-    using SC = StageCfg<T, INFMT, LOG2F>;
+    using C = SmemCfg<T, LOG2F, VAR>;
+    using SC = StageCfg<T, INFMT, LOG2F, VAR>;
     using IN = Ingest<T, INFMT>;
     constexpr int P = C::P, F = C::F, NT = C::NT, TEAMS = C::TEAMS, LOG2P = C::LOG2P, STG = SC::STG;
     constexpr int L0 = stage_l<LOG2F, LOG2P>(0);
@@ -145,12 +149,12 @@ curscan_smem_kernel(const ScanParams p) {
 
     // tables that stay in registers for the life of the CTA (fast path)
     T win[C::REGTAB ? P : 1];
-    cx<T> twl[(C::REGTAB && C::NTW > 0) ? C::NTW : 1];
+    cx<T> twl[(C::TWREG && C::NTW > 0) ? C::NTW : 1];
     if constexpr (C::REGTAB) {
 #pragma unroll
         for (int m = 0; m < P; ++m) win[m] = gwin[tid + NT * m];
-        load_twiddles<T, LOG2F, LOG2P>(twl, gtw, tid);
     }
+    if constexpr (C::TWREG) load_twiddles<T, LOG2F, LOG2P>(twl, gtw, tid);
 
     const T u8off = (T)p.u8Offset, u8scale = (T)p.u8Scale;
     const T linScale = (T)p.linScale;
@@ -221,9 +225,9 @@ curscan_smem_kernel(const ScanParams p) {
                     __syncthreads();
                     if (threadIdx.x == 0 && g + STG < totalFrames) issue(g + STG);
                 };
-                fft_tail_first<T, LOG2F, LOG2P, C::REGTAB, C::DBUF, L0>(b, twl, gtw, bufA, bufB, tid, sync, sync_and_refill);
+                fft_tail_first<T, LOG2F, LOG2P, C::TWREG, C::DBUF, L0>(b, twl, gtw, bufA, bufB, tid, sync, sync_and_refill);
             } else {
-                fft_tail<T, LOG2F, LOG2P, C::REGTAB, C::DBUF, L0, 0, 0>(b, twl, gtw, bufA, bufB, tid, sync);
+                fft_tail<T, LOG2F, LOG2P, C::TWREG, C::DBUF, L0, 0, 0>(b, twl, gtw, bufA, bufB, tid, sync);
             }
             if constexpr (C::DBUF && (C::NX & 1)) { cx<T>* t = bufA; bufA = bufB; bufB = t; }
             // |X| and cumulate over the frames of this scan (data_cumu, K:124-147); normalisation is applied once per scan
@@ -249,6 +253,18 @@ curscan_smem_kernel(const ScanParams p) {
         // scratch row for the waterfall compress: bufA, the buffer the last exchange did NOT use (see above)
         T* erow = reinterpret_cast<T*>(bufA);
         if (needRow && !C::DBUF) __syncthreads();
+        // running Max/Min of this team (K:471-474): fetch all partials in one batch so the loads overlap the dB math
+        T* __restrict__ wmax = reinterpret_cast<T*>(p.wsMax) + (int64_t)slot * F;
+        T* __restrict__ wmin = reinterpret_cast<T*>(p.wsMin) + (int64_t)slot * F;
+        T omax[P], omin[P];
+        if (p.wantStats && it > 0) {
+#pragma unroll
+            for (int m = 0; m < P; ++m) {
+                const int j = (tid + NT * m) ^ (F >> 1);
+                omax[m] = wmax[j];
+                omin[m] = wmin[j];
+            }
+        }
 #pragma unroll
         for (int m = 0; m < P; ++m) {
             const int j = (tid + NT * m) ^ (F >> 1);
@@ -260,14 +276,12 @@ curscan_smem_kernel(const ScanParams p) {
                 if (p.infToZero && isinf(db)) db = (T)0;
                 if (valid && p.rowsKind == KSPEC_ROWS_DB) rows[scan * F + j] = db;
                 if (p.wantStats) {
-                    T* __restrict__ wmax = reinterpret_cast<T*>(p.wsMax) + (int64_t)slot * F;
-                    T* __restrict__ wmin = reinterpret_cast<T*>(p.wsMin) + (int64_t)slot * F;
                     if (it == 0) {
                         wmax[j] = valid ? db : -pos_inf<T>();
                         wmin[j] = valid ? db : pos_inf<T>();
                     } else if (valid) {
-                        wmax[j] = fmax(wmax[j], db);
-                        wmin[j] = fmin(wmin[j], db);
+                        wmax[j] = fmax(omax[m], db);
+                        wmin[j] = fmin(omin[m], db);
                     }
                     const int64_t ar = scan - (p.nScans - p.avgWin);
                     if (valid && ar >= 0) reinterpret_cast<T*>(p.avgRows)[ar * F + j] = db;
@@ -298,11 +312,11 @@ curscan_smem_kernel(const ScanParams p) {
     }
 }
 
-template <typename T, int INFMT, int LOG2F>
+template <typename T, int INFMT, int LOG2F, int VAR = 0>
 static int launch_smem_one(const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info) {
-    using C = SmemCfg<T, LOG2F>;
-    using SC = StageCfg<T, INFMT, LOG2F>;
-    auto k = curscan_smem_kernel<T, INFMT, LOG2F>;
+    using C = SmemCfg<T, LOG2F, VAR>;
+    using SC = StageCfg<T, INFMT, LOG2F, VAR>;
+    auto k = curscan_smem_kernel<T, INFMT, LOG2F, VAR>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SC::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     if (info) {

@@ -149,19 +149,34 @@ template <typename T, int P, int R, int NT, int LNS>
 __device__ __forceinline__ void scatter(const cx<T> (&b)[P], cx<T>* sm, int tid) {
     constexpr int V = P / R;
     constexpr int NS = 1 << LNS;
+    // pad_idx(base + t*NS) == pad_idx(base) + t*NS + (t*NS >> 4) whenever the low 4 bits of base cannot carry into
+    // the padding term: one base address per butterfly, compile-time offsets per element (no per-element integer math)
+    constexpr bool FAST = (NS >= 16) || ((NS * R) % 16 == 0);
 #pragma unroll
     for (int v = 0; v < V; ++v) {
         const int j = tid + v * NT;
         const int base = ((j >> LNS) << LNS) * R + (j & (NS - 1));
+        if constexpr (FAST) {
+            cx<T>* q = sm + pad_idx(base);
 #pragma unroll
-        for (int t = 0; t < R; ++t) sm[pad_idx(base + t * NS)] = b[v + t * V];
+            for (int t = 0; t < R; ++t) q[t * NS + ((t * NS) >> 4)] = b[v + t * V];
+        } else {
+#pragma unroll
+            for (int t = 0; t < R; ++t) sm[pad_idx(base + t * NS)] = b[v + t * V];
+        }
     }
 }
 
 template <typename T, int P, int NT>
 __device__ __forceinline__ void gather(cx<T> (&b)[P], const cx<T>* sm, int tid) {
+    if constexpr (NT % 16 == 0) {
+        const cx<T>* q = sm + pad_idx(tid);
 #pragma unroll
-    for (int m = 0; m < P; ++m) b[m] = sm[pad_idx(tid + NT * m)];
+        for (int m = 0; m < P; ++m) b[m] = q[m * (NT + NT / 16)];
+    } else {
+#pragma unroll
+        for (int m = 0; m < P; ++m) b[m] = sm[pad_idx(tid + NT * m)];
+    }
 }
 
 // fill the per-thread twiddle list for all stages >= 1 from the global table tw[k] = exp(-2 pi i k / F)

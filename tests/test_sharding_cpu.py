@@ -1,0 +1,87 @@
+"""Host logic of the multi-GPU path on CPU: scan-range sharding, the global halving-average weights, and the
+MAX / MIN / SUM combination -- once with plain numpy and once across two real processes (torch.distributed, gloo,
+world_size 2), which is what kspec_comm_allreduce_stats does over NCCL on the GPU box."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from kspec.sharding import avg_weights, combine_stats, shard_bounds
+from oracle import kspec_oracle as O
+
+
+def test_shard_bounds_cover_everything_once():
+    for n, w in ((146, 8), (2197, 4), (5, 8), (16384, 3), (1, 1)):
+        b = shard_bounds(n, w)
+        assert b[0][0] == 0 and b[-1][1] == n and all(x[1] == y[0] for x, y in zip(b[:-1], b[1:]))
+        sizes = [y - x for x, y in b]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_avg_weights_equal_the_recurrence():
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 15, 64, 100):
+        x = rng.normal(size=(n, 7)) * 20 - 50
+        a = None
+        for row in x:
+            a = O.cumulate("AVG", a, row)
+        assert np.allclose(avg_weights(n) @ x, a, rtol=0, atol=1e-12)
+        assert abs(avg_weights(n).sum() - 1.0) < 1e-15
+
+
+def _partial(rows, a, b, n):
+    """what kspec_zerospan_batch returns for shard [a,b) of n scans (float64 semantics)"""
+    w = avg_weights(n)[a:b]
+    return dict(max=rows[a:b].max(axis=0), min=rows[a:b].min(axis=0), avg=w @ rows[a:b])
+
+
+def test_combine_equals_sequential():
+    rng = np.random.default_rng(1)
+    rows = rng.normal(size=(40, 33)) * 10 - 60
+    ref = O.zerospan(10 ** ((rows + 19.1) / 10), 19.1, 33, "RAW")
+    for w in (1, 2, 4, 8):
+        parts = [_partial(rows, a, b, 40) for a, b in shard_bounds(40, w)]
+        got = combine_stats(parts)
+        assert np.allclose(got["max"], ref["max"], atol=1e-9) and np.allclose(got["min"], ref["min"], atol=1e-9)
+        assert np.allclose(got["avg"], ref["avg"], atol=1e-9)
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(1)
+    rows = rng.normal(size=(40, 33)) * 10 - 60
+    a, b = shard_bounds(40, world)[rank]
+    p = _partial(rows, a, b, 40)
+    mx, mn, av = (torch.from_numpy(p[k].copy()) for k in ("max", "min", "avg"))
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+    dist.all_reduce(av, op=dist.ReduceOp.SUM)
+    q.put((rank, mx.numpy(), mn.numpy(), av.numpy()))
+    dist.destroy_process_group()
+
+
+def test_two_process_gloo_allreduce_matches_single_process():
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(1)
+    rows = rng.normal(size=(40, 33)) * 10 - 60
+    ref = O.zerospan(10 ** ((rows + 19.1) / 10), 19.1, 33, "RAW")
+    for _, mx, mn, av in res:
+        assert np.allclose(mx, ref["max"], atol=1e-9) and np.allclose(mn, ref["min"], atol=1e-9)
+        assert np.allclose(av, ref["avg"], atol=1e-9)
