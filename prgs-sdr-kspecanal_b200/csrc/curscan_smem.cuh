@@ -20,19 +20,23 @@ namespace kspec {
 
 // VAR selects a tuning variant of the same kernel (A/B experiments, see profiles/README.md):
 //   0 production   1 twiddles via L1 instead of registers, 4 CTAs/SM   2 as 1 without TMA staging   3 as 0 with one stage
+//   5 as 0 with 2 CTAs/SM (255 registers)   6 as 3 with the twiddles in a linearised shared-memory table
+//   4 one 512-thread CTA per SM = four independent 128-thread teams (named barriers) sharing one shared-memory twiddle table
 template <typename T, int LOG2F, int VAR = 0> struct SmemCfg {
     static constexpr int LOG2P = LOG2F >= 7 ? 4 : (LOG2F >= 5 ? 3 : 2);
     static constexpr int P = 1 << LOG2P, F = 1 << LOG2F, NT = F / P;
-    static constexpr int CTA = NT < 128 ? 128 : NT;
+    static constexpr bool MULTI = (VAR == 4) && NT >= 32;  // teams of whole warps that never wait for each other
+    static constexpr int CTA = MULTI ? 4 * NT : (NT < 128 ? 128 : NT);
     static constexpr int TEAMS = CTA / NT;
     static constexpr bool F32 = sizeof(T) == 4;
     static constexpr bool REGTAB = F32 && LOG2F <= 11;   // window (and, by default, twiddles) live in registers across frames
-    static constexpr bool TWREG = REGTAB && !(VAR == 1 || VAR == 2);
+    static constexpr bool TWREG = REGTAB && !(VAR == 1 || VAR == 2 || VAR == 6 || MULTI);
+    static constexpr bool TWSMEM = MULTI || VAR == 6;    // twiddle table copied to shared memory once per CTA
     static constexpr int FPAD = padded_len(F);
     static constexpr int BUF_BYTES = FPAD * (int)sizeof(cx<T>) * TEAMS;
     static constexpr bool DBUF = 2 * BUF_BYTES <= 160 * 1024;
     static constexpr int SMEM_BYTES = (DBUF ? 2 : 1) * BUF_BYTES;
-    static constexpr int MINB = (VAR == 1 || VAR == 2) ? 4 : (CTA == 128 ? (F32 ? 3 : 2) : (CTA == 256 ? (F32 ? 2 : 1) : 1));
+    static constexpr int MINB = MULTI ? 1 : (VAR == 5) ? 2 : (VAR == 1 || VAR == 2) ? 4 : (CTA == 128 ? (F32 ? 3 : 2) : (CTA == 256 ? (F32 ? 2 : 1) : 1));
     static constexpr int NTW = twiddle_count<LOG2F, LOG2P>();
     static constexpr int NX = exchange_count<LOG2F, LOG2P>();
 };
@@ -52,7 +56,7 @@ template <typename T> struct Ingest<T, KSPEC_IN_U8_IQ> {
 template <typename T> struct Ingest<T, KSPEC_IN_C64> {
     static constexpr int ELEM_BYTES = 8;
     typedef float2 raw_t;
-    static __device__ __forceinline__ cx<T> conv(float2 v, T w, T, T) { return mkcx<T>((T)v.x * w, (T)v.y * w); }
+    static __device__ __forceinline__ cx<T> conv(float2 v, T w, T, T) { return cscale(mkcx<T>((T)v.x, (T)v.y), w); }
     static __device__ __forceinline__ cx<T> load(const void* base, int64_t i, T w, T off, T scale) {
         return conv(__ldg(reinterpret_cast<const float2*>(base) + i), w, off, scale);
     }
@@ -60,7 +64,7 @@ template <typename T> struct Ingest<T, KSPEC_IN_C64> {
 template <typename T> struct Ingest<T, KSPEC_IN_C128> {
     static constexpr int ELEM_BYTES = 16;
     typedef double2 raw_t;
-    static __device__ __forceinline__ cx<T> conv(double2 v, T w, T, T) { return mkcx<T>((T)v.x * w, (T)v.y * w); }
+    static __device__ __forceinline__ cx<T> conv(double2 v, T w, T, T) { return cscale(mkcx<T>((T)v.x, (T)v.y), w); }
     static __device__ __forceinline__ cx<T> load(const void* base, int64_t i, T w, T off, T scale) {
         return conv(__ldg(reinterpret_cast<const double2*>(base) + i), w, off, scale);
     }
@@ -78,12 +82,14 @@ template <typename T, int INFMT, int LOG2F, int VAR = 0> struct StageCfg {
     static constexpr int SLACK = EB >= 16 ? 0 : 16 / EB;                       // elements
     static constexpr int STAGE_BYTES = ((C::F + SLACK) * EB + 127) / 128 * 128;
     static constexpr int BUDGET = 225 * 1024;
-    static constexpr bool OK = C::TEAMS == 1 && C::DBUF;
+    static constexpr bool OK = (C::TEAMS == 1 || C::MULTI) && C::DBUF;
     static constexpr int STG_AUTO = !OK ? 0 : (C::MINB * (C::SMEM_BYTES + 2 * STAGE_BYTES + 1024) <= BUDGET ? 2
                                             : (C::MINB * (C::SMEM_BYTES + STAGE_BYTES + 1024) <= BUDGET ? 1 : 0));
-    static constexpr int STG = VAR == 2 ? 0 : (VAR == 3 ? (STG_AUTO > 1 ? 1 : STG_AUTO) : STG_AUTO);
+    static constexpr int STG = VAR == 2 ? 0 : (C::MULTI ? 1 : ((VAR == 3 || VAR == 6) ? (STG_AUTO > 1 ? 1 : STG_AUTO) : STG_AUTO));
     static constexpr int EX_BYTES = (C::SMEM_BYTES + 127) / 128 * 128;
-    static constexpr int SMEM_BYTES = EX_BYTES + STG * STAGE_BYTES;
+    static constexpr int STAGE_TEAMS = C::MULTI ? C::TEAMS : 1;
+    static constexpr int TW_OFS = EX_BYTES + STAGE_TEAMS * STG * STAGE_BYTES;
+    static constexpr int SMEM_BYTES = TW_OFS + (C::TWSMEM ? C::F * (int)sizeof(cx<T>) : 0);
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -109,7 +115,8 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 }
 
 __device__ __forceinline__ float kabs(float2 a) {
-    const float s = a.x * a.x + a.y * a.y;
+    const float2 q = __fmul2_rn(a, a);
+    const float s = q.x + q.y;
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s));
     return r;
@@ -133,19 +140,32 @@ curscan_smem_kernel(const ScanParams p) {
     constexpr int L0 = stage_l<LOG2F, LOG2P>(0);
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t mbar[2];
+    __shared__ uint64_t mbar_all[SC::STAGE_TEAMS][2];
     const int team = (TEAMS > 1) ? (threadIdx.x / NT) : 0;
     const int tid = (TEAMS > 1) ? (threadIdx.x % NT) : threadIdx.x;
+    uint64_t* mbar = mbar_all[C::MULTI ? team : 0];
+    const bool leader = C::MULTI ? (tid == 0) : (threadIdx.x == 0);      // issues this team's bulk copies
     // two exchange buffers per team (bufA/bufB) when they fit, else one.  Exchange x of a frame uses bufA for even
     // x and bufB for odd x; with an odd exchange count the roles swap after every frame, so a buffer is never
     // rewritten before a full barrier separates it from its last readers.
     cx<T>* bufA = reinterpret_cast<cx<T>*>(smem_raw) + team * C::FPAD;
     cx<T>* bufB = C::DBUF ? bufA + TEAMS * C::FPAD : bufA;
-    unsigned char* stage0 = smem_raw + SC::EX_BYTES;
+    unsigned char* stage0 = smem_raw + SC::EX_BYTES + (C::MULTI ? team * STG * SC::STAGE_BYTES : 0);
 
     const T* __restrict__ gwin = reinterpret_cast<const T*>(p.win);
     const cx<T>* __restrict__ gtw = reinterpret_cast<const cx<T>*>(p.tw);
-    auto sync = [] { __syncthreads(); };
+    // team barrier: the whole CTA, or (independent teams) a named barrier over this team's NT threads
+    auto sync = [team] {
+        if constexpr (C::MULTI) asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(NT) : "memory");
+        else __syncthreads();
+        (void)team;
+    };
+    const cx<T>* twtab = gtw;
+    if constexpr (C::TWSMEM) {
+        cx<T>* stw = reinterpret_cast<cx<T>*>(smem_raw + SC::TW_OFS);
+        build_lin_twiddles<T, LOG2F, LOG2P>(stw, gtw, threadIdx.x, C::CTA);
+        twtab = stw;
+    }
 
     // tables that stay in registers for the life of the CTA (fast path)
     T win[C::REGTAB ? P : 1];
@@ -178,13 +198,15 @@ curscan_smem_kernel(const ScanParams p) {
         tma_load_1d(stage0 + s * SC::STAGE_BYTES, reinterpret_cast<const unsigned char*>(p.samples) + e0a * SC::EB, bytes, &mbar[s]);
     };
     if constexpr (STG > 0) {
-        if (threadIdx.x == 0) {
+        if (leader) {
             mbar_init(&mbar[0], 1);
             mbar_init(&mbar[1], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
+    }
+    if constexpr (STG > 0 || C::TWSMEM) __syncthreads();
+    if constexpr (STG > 0) {
+        if (leader) {
             for (int g = 0; g < STG && g < totalFrames; ++g) issue(g);
         }
     }
@@ -222,12 +244,12 @@ curscan_smem_kernel(const ScanParams p) {
             if constexpr (STG > 0) {
                 // the first exchange's barrier also tells thread 0 that every thread has consumed the stage buffer
                 auto sync_and_refill = [&] {
-                    __syncthreads();
-                    if (threadIdx.x == 0 && g + STG < totalFrames) issue(g + STG);
+                    sync();
+                    if (leader && g + STG < totalFrames) issue(g + STG);
                 };
-                fft_tail_first<T, LOG2F, LOG2P, C::TWREG, C::DBUF, L0>(b, twl, gtw, bufA, bufB, tid, sync, sync_and_refill);
+                fft_tail_first<T, LOG2F, LOG2P, C::TWREG, C::DBUF, L0, !C::TWSMEM>(b, twl, twtab, bufA, bufB, tid, sync, sync_and_refill);
             } else {
-                fft_tail<T, LOG2F, LOG2P, C::TWREG, C::DBUF, L0, 0, 0>(b, twl, gtw, bufA, bufB, tid, sync);
+                fft_tail<T, LOG2F, LOG2P, C::TWREG, C::DBUF, L0, 0, 0, !C::TWSMEM>(b, twl, twtab, bufA, bufB, tid, sync);
             }
             if constexpr (C::DBUF && (C::NX & 1)) { cx<T>* t = bufA; bufA = bufB; bufB = t; }
             // |X| and cumulate over the frames of this scan (data_cumu, K:124-147); normalisation is applied once per scan
@@ -252,7 +274,7 @@ curscan_smem_kernel(const ScanParams p) {
         const bool needRow = (p.hm != nullptr);
         // scratch row for the waterfall compress: bufA, the buffer the last exchange did NOT use (see above)
         T* erow = reinterpret_cast<T*>(bufA);
-        if (needRow && !C::DBUF) __syncthreads();
+        if (needRow && !C::DBUF) sync();
         // running Max/Min of this team (K:471-474): fetch all partials in one batch so the loads overlap the dB math
         T* __restrict__ wmax = reinterpret_cast<T*>(p.wsMax) + (int64_t)slot * F;
         T* __restrict__ wmin = reinterpret_cast<T*>(p.wsMin) + (int64_t)slot * F;
@@ -290,7 +312,7 @@ curscan_smem_kernel(const ScanParams p) {
             }
         }
         if (needRow) {
-            __syncthreads();
+            sync();
             // _data_plotcompress (K:184-200): W groups of g adjacent bins
             const int W = p.hmW, gsz = F / W;
             T* __restrict__ hm = reinterpret_cast<T*>(p.hm);
@@ -307,7 +329,7 @@ curscan_smem_kernel(const ScanParams p) {
                 }
                 if (valid) hm[scan * W + w] = r;
             }
-            __syncthreads();
+            sync();
         }
     }
 }

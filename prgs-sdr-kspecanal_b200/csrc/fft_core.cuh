@@ -26,19 +26,29 @@ template <typename T> using cx = typename CxOf<T>::type;
 
 template <typename T> __host__ __device__ __forceinline__ cx<T> mkcx(T x, T y) { cx<T> r; r.x = x; r.y = y; return r; }
 
-#define KSPEC_CX_OPS(C)                                                                                   \
-    __device__ __forceinline__ C operator+(C a, C b) { C r; r.x = a.x + b.x; r.y = a.y + b.y; return r; } \
-    __device__ __forceinline__ C operator-(C a, C b) { C r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
-KSPEC_CX_OPS(float2)
-KSPEC_CX_OPS(double2)
-#undef KSPEC_CX_OPS
+// complex float = one 64-bit register pair (re, im): Blackwell's packed FP32 instructions (FADD2 / FMUL2 / FFMA2, PTX
+// add/mul/fma.f32x2) operate on the pair in one issue slot, and their operand modifiers make the complex idioms free:
+// negation, half swap with per-half sign (".LO_HI.NP": multiplication by +-i) and scalar broadcast (".F32").
+//   complex add / sub        1 FADD2            (scalar code: 2 FADD)
+//   a + (+-i) b              1 FADD2            (2 FADD)
+//   real scale               1 FMUL2            (2 FMUL)
+//   complex multiply         FMUL2 + FFMA2      (2 FMUL + 2 FFMA)
+__device__ __forceinline__ float2 operator+(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 operator-(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ double2 operator+(double2 a, double2 b) { double2 r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
+__device__ __forceinline__ double2 operator-(double2 a, double2 b) { double2 r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
 
-template <typename C> __device__ __forceinline__ C cmul(C a, C w) {
-    C r;
+__device__ __forceinline__ float2 cmul(float2 a, float2 w) {
+    return __ffma2_rn(make_float2(-a.y, a.x), make_float2(w.y, w.y), __fmul2_rn(a, make_float2(w.x, w.x)));
+}
+__device__ __forceinline__ double2 cmul(double2 a, double2 w) {
+    double2 r;
     r.x = a.x * w.x - a.y * w.y;
     r.y = a.x * w.y + a.y * w.x;
     return r;
 }
+__device__ __forceinline__ float2 cscale(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+__device__ __forceinline__ double2 cscale(double2 a, double s) { a.x *= s; a.y *= s; return a; }
 template <typename C> __device__ __forceinline__ C mul_mi(C a) { C r; r.x = a.y;  r.y = -a.x; return r; }  // a * (-i)
 template <typename C> __device__ __forceinline__ C mul_pi(C a) { C r; r.x = -a.y; r.y = a.x;  return r; }  // a * (+i)
 
@@ -59,9 +69,9 @@ template <typename T> __device__ __forceinline__ void dft8(cx<T> (&x)[8]) {
     dft4<T>(x[0], x[2], x[4], x[6]);
     dft4<T>(x[1], x[3], x[5], x[7]);
     // odd outputs times W8^k, k = 0..3
-    cx<T> o1 = mkcx<T>((x[3].x + x[3].y) * h, (x[3].y - x[3].x) * h);     // * (1-i)/sqrt2
+    cx<T> o1 = cmul(x[3], mkcx<T>(h, -h));                                // * (1-i)/sqrt2
     cx<T> o2 = mul_mi(x[5]);                                              // * -i
-    cx<T> o3 = mkcx<T>((x[7].y - x[7].x) * h, -(x[7].x + x[7].y) * h);    // * (-1-i)/sqrt2
+    cx<T> o3 = cmul(x[7], mkcx<T>(-h, -h));                               // * (-1-i)/sqrt2
     cx<T> e0 = x[0], e1 = x[2], e2 = x[4], e3 = x[6], o0 = x[1];
     x[0] = e0 + o0; x[4] = e0 - o0;
     x[1] = e1 + o1; x[5] = e1 - o1;
@@ -76,13 +86,13 @@ template <typename T> __device__ __forceinline__ void dft16(cx<T> (&x)[16]) {
     for (int n2 = 0; n2 < 4; ++n2) dft4<T>(x[n2], x[4 + n2], x[8 + n2], x[12 + n2]);   // -> y[k1][n2] at x[4*k1+n2]
     // twiddles W16^(n2*k1)
     x[5]  = cmul(x[5],  mkcx<T>(c1, -s1));                                    // W^1
-    x[6]  = mkcx<T>((x[6].x + x[6].y) * h, (x[6].y - x[6].x) * h);            // W^2
+    x[6]  = cmul(x[6],  mkcx<T>(h, -h));                                      // W^2
     x[7]  = cmul(x[7],  mkcx<T>(s1, -c1));                                    // W^3
-    x[9]  = mkcx<T>((x[9].x + x[9].y) * h, (x[9].y - x[9].x) * h);            // W^2
+    x[9]  = cmul(x[9],  mkcx<T>(h, -h));                                      // W^2
     x[10] = mul_mi(x[10]);                                                    // W^4
-    x[11] = mkcx<T>((x[11].y - x[11].x) * h, -(x[11].x + x[11].y) * h);       // W^6
+    x[11] = cmul(x[11], mkcx<T>(-h, -h));                                     // W^6
     x[13] = cmul(x[13], mkcx<T>(s1, -c1));                                    // W^3
-    x[14] = mkcx<T>((x[14].y - x[14].x) * h, -(x[14].x + x[14].y) * h);       // W^6
+    x[14] = cmul(x[14], mkcx<T>(-h, -h));                                     // W^6
     x[15] = cmul(x[15], mkcx<T>(-c1, s1));                                    // W^9
 #pragma unroll
     for (int k1 = 0; k1 < 4; ++k1) dft4<T>(x[4 * k1], x[4 * k1 + 1], x[4 * k1 + 2], x[4 * k1 + 3]);  // -> X[k1+4*k2] at x[4*k1+k2]
@@ -204,7 +214,42 @@ __device__ __forceinline__ void load_twiddles(cx<T>* dst, const cx<T>* __restric
 //            (global / L1) at every use.
 //   DBUF   : two exchange buffers (one barrier per exchange) or one (two barriers).
 // `sync` is a functor: team-wide barrier.
-template <typename T, int LOG2F, int LOG2P, bool TWREGS, bool DBUF, int LNS, int OFS, int XI, typename Sync>
+// Twiddle sources for the stages >= 1 when they are not register resident:
+//   TWLDG  = true : the natural table tw[k] = exp(-2 pi i k/F) in global memory, read through the read-only path;
+//   TWLDG  = false: a "linearised" copy in shared memory, one block per stage laid out [t-1][k], k = j mod Ns, so that
+//                   the lanes of a warp read consecutive words (the natural table would be read with stride t*F/(Ns*R):
+//                   8..16-way bank conflicts).  Block s starts at tw_lin_offset(lns_s); the total is F - R0 entries.
+template <int LOG2F, int LOG2P> __host__ __device__ constexpr int tw_lin_offset(int lns) {
+    int ofs = 0, cur = stage_l<LOG2F, LOG2P>(0);
+    while (cur < lns) {
+        int l = stage_l<LOG2F, LOG2P>(cur);
+        ofs += ((1 << l) - 1) << cur;
+        cur += l;
+    }
+    return ofs;
+}
+
+template <typename T, int LOG2F, int LOG2P, int LNS = stage_l<LOG2F, LOG2P>(0)>
+__device__ __forceinline__ void build_lin_twiddles(cx<T>* dst, const cx<T>* __restrict__ table, int thread, int nthreads) {
+    if constexpr (LNS < LOG2F) {
+        constexpr int L = stage_l<LOG2F, LOG2P>(LNS), R = 1 << L, NS = 1 << LNS;
+        constexpr int OFS = tw_lin_offset<LOG2F, LOG2P>(LNS);
+        for (int i = thread; i < (R - 1) * NS; i += nthreads) {
+            const int t = (i >> LNS) + 1, k = i & (NS - 1);
+            dst[OFS + i] = table[(t * k) << (LOG2F - LNS - L)];
+        }
+        build_lin_twiddles<T, LOG2F, LOG2P, LNS + L>(dst, table, thread, nthreads);
+    }
+}
+
+template <bool LDG, int LOG2F, int LOG2P, int LNS, typename C>
+__device__ __forceinline__ C ld_tw(const C* __restrict__ table, int t, int k) {
+    constexpr int L = stage_l<LOG2F, LOG2P>(LNS);
+    if constexpr (LDG) return __ldg(&table[(t * k) << (LOG2F - LNS - L)]);
+    else return table[tw_lin_offset<LOG2F, LOG2P>(LNS) + ((t - 1) << LNS) + k];
+}
+
+template <typename T, int LOG2F, int LOG2P, bool TWREGS, bool DBUF, int LNS, int OFS, int XI, bool TWLDG = true, typename Sync>
 __device__ __forceinline__ void fft_tail(cx<T> (&b)[1 << LOG2P], const cx<T>* twl, const cx<T>* __restrict__ table,
                                          cx<T>* buf0, cx<T>* buf1, int tid, Sync sync) {
     if constexpr (LNS < LOG2F) {
@@ -225,17 +270,17 @@ __device__ __forceinline__ void fft_tail(cx<T> (&b)[1 << LOG2P], const cx<T>* tw
             for (int v = 0; v < V; ++v) {
                 const int k = (tid + v * NT) & ((1 << LNS) - 1);
 #pragma unroll
-                for (int t = 1; t < R; ++t) tw[v * (R - 1) + (t - 1)] = __ldg(&table[(t * k) << (LOG2F - LNS - L)]);
+                for (int t = 1; t < R; ++t) tw[v * (R - 1) + (t - 1)] = ld_tw<TWLDG, LOG2F, LOG2P, LNS>(table, t, k);
             }
             butterflies<T, P, R, true>(b, tw);
         }
-        fft_tail<T, LOG2F, LOG2P, TWREGS, DBUF, LNS + L, OFS + V * (R - 1), XI + 1>(b, twl, table, buf0, buf1, tid, sync);
+        fft_tail<T, LOG2F, LOG2P, TWREGS, DBUF, LNS + L, OFS + V * (R - 1), XI + 1, TWLDG>(b, twl, table, buf0, buf1, tid, sync);
     }
 }
 
 // Same as fft_tail, but the barrier of the FIRST exchange is `syncFirst` (the staged kernel re-arms its TMA prefetch
 // there: once every thread is past that barrier the stage buffer has been fully consumed).
-template <typename T, int LOG2F, int LOG2P, bool TWREGS, bool DBUF, int LNS, typename Sync, typename SyncFirst>
+template <typename T, int LOG2F, int LOG2P, bool TWREGS, bool DBUF, int LNS, bool TWLDG = true, typename Sync, typename SyncFirst>
 __device__ __forceinline__ void fft_tail_first(cx<T> (&b)[1 << LOG2P], const cx<T>* twl, const cx<T>* __restrict__ table,
                                                cx<T>* buf0, cx<T>* buf1, int tid, Sync sync, SyncFirst syncFirst) {
     static_assert(LNS < LOG2F, "needs at least one exchange");
@@ -253,11 +298,11 @@ __device__ __forceinline__ void fft_tail_first(cx<T> (&b)[1 << LOG2P], const cx<
         for (int v = 0; v < V; ++v) {
             const int k = (tid + v * NT) & ((1 << LNS) - 1);
 #pragma unroll
-            for (int t = 1; t < R; ++t) tw[v * (R - 1) + (t - 1)] = __ldg(&table[(t * k) << (LOG2F - LNS - L)]);
+            for (int t = 1; t < R; ++t) tw[v * (R - 1) + (t - 1)] = ld_tw<TWLDG, LOG2F, LOG2P, LNS>(table, t, k);
         }
         butterflies<T, P, R, true>(b, tw);
     }
-    fft_tail<T, LOG2F, LOG2P, TWREGS, DBUF, LNS + L, V * (R - 1), 1>(b, twl, table, buf0, buf1, tid, sync);
+    fft_tail<T, LOG2F, LOG2P, TWREGS, DBUF, LNS + L, V * (R - 1), 1, TWLDG>(b, twl, table, buf0, buf1, tid, sync);
 }
 
 }  // namespace kspec

@@ -5,6 +5,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <new>
 
 namespace kspec {
@@ -63,7 +64,8 @@ struct kspec_plan {
     cudaStream_t st = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int smCount = 0;
-    SmemKernelInfo ki{};
+    SmemKernelInfo ki{};          // base variant of the fused kernel
+    SmemKernelInfo kiMulti{};     // multi-team variant (ctasPerSm == 0: not available for this shape)
     int64_t convSize = 0;
     BigFft* big = nullptr;
     int64_t launches = 0;
@@ -89,12 +91,13 @@ constexpr size_t TAIL_PAD = 64;   // bytes a staged bulk copy may read past the 
 size_t in_elem_bytes(int fmt) { return fmt == KSPEC_IN_U8_IQ ? 2 : (fmt == KSPEC_IN_C64 ? 8 : 16); }
 size_t real_bytes(int prec) { return prec == KSPEC_PREC_F32 ? 4 : 8; }
 
-int launch_smem(const kspec_plan* pl, const ScanParams& p, int grid, SmemKernelInfo* info) {
+int launch_smem(const kspec_plan* pl, int variant, const ScanParams& p, int grid, SmemKernelInfo* info) {
     const bool f32 = pl->prec == KSPEC_PREC_F32;
+    const int l = pl->log2F;
     switch (pl->inFmt) {
-        case KSPEC_IN_U8_IQ: return f32 ? launch_smem_f32_u8(pl->log2F, p, grid, pl->st, info) : launch_smem_f64_u8(pl->log2F, p, grid, pl->st, info);
-        case KSPEC_IN_C64:   return f32 ? launch_smem_f32_c64(pl->log2F, p, grid, pl->st, info) : launch_smem_f64_c64(pl->log2F, p, grid, pl->st, info);
-        default:             return f32 ? launch_smem_f32_c128(pl->log2F, p, grid, pl->st, info) : launch_smem_f64_c128(pl->log2F, p, grid, pl->st, info);
+        case KSPEC_IN_U8_IQ: return f32 ? launch_smem_f32_u8(l, variant, p, grid, pl->st, info) : launch_smem_f64_u8(l, variant, p, grid, pl->st, info);
+        case KSPEC_IN_C64:   return f32 ? launch_smem_f32_c64(l, variant, p, grid, pl->st, info) : launch_smem_f64_c64(l, variant, p, grid, pl->st, info);
+        default:             return f32 ? launch_smem_f32_c128(l, variant, p, grid, pl->st, info) : launch_smem_f64_c128(l, variant, p, grid, pl->st, info);
     }
 }
 
@@ -125,9 +128,13 @@ ScanParams base_params(const kspec_plan* pl, const void* dSamples, int64_t nScan
 int run_engine(kspec_plan* pl, ScanParams& p, int* slotsOut) {
     const size_t rb = real_bytes(pl->prec);
     if (pl->path == KSPEC_PATH_SMEM) {
-        const int teams = pl->ki.teams;
+        // large batches of the headline shape run four independent teams per CTA (one CTA per SM); small ones the base layout
+        const bool multi = pl->kiMulti.ctasPerSm > 0 && p.nScans >= (int64_t)2 * pl->smCount * pl->kiMulti.teams;
+        const SmemKernelInfo& ki = multi ? pl->kiMulti : pl->ki;
+        const int variant = multi ? SMEM_VARIANT_MULTI : SMEM_VARIANT_BASE;
+        const int teams = ki.teams;
         int64_t need = (p.nScans + teams - 1) / teams;
-        int64_t cap = (int64_t)pl->smCount * (pl->ki.ctasPerSm > 0 ? pl->ki.ctasPerSm : 1);
+        int64_t cap = (int64_t)pl->smCount * (ki.ctasPerSm > 0 ? ki.ctasPerSm : 1);
         int grid = (int)(need < cap ? need : cap);
         if (grid < 1) grid = 1;
         const int slots = grid * teams;
@@ -140,7 +147,7 @@ int run_engine(kspec_plan* pl, ScanParams& p, int* slotsOut) {
         }
         const int ks = (int)(pl->kcount % kspec_plan::KT);
         cudaEventRecord(pl->kev[ks][0], pl->st);
-        int e = launch_smem(pl, p, grid, nullptr);
+        int e = launch_smem(pl, variant, p, grid, nullptr);
         cudaEventRecord(pl->kev[ks][1], pl->st);
         pl->kcount += 1;
         if (e != 0) { set_error("scan kernel launch failed: %s", cudaGetErrorString((cudaError_t)e)); return KSPEC_ERR_CUDA; }
@@ -292,7 +299,8 @@ int kspec_plan_create(kspec_plan** out, int fftSize, int64_t fullSize, double no
             cudaMemcpy(pl->dTw, tw.data(), tw.size() * 8, cudaMemcpyHostToDevice);
         }
         ScanParams dummy{};
-        if (launch_smem(pl, dummy, 0, &pl->ki) != 0) { set_error("kernel attribute query failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(KSPEC_ERR_CUDA); }
+        if (launch_smem(pl, SMEM_VARIANT_MULTI, dummy, 0, &pl->kiMulti) != 0) { cudaGetLastError(); pl->kiMulti = SmemKernelInfo{}; }
+        if (launch_smem(pl, SMEM_VARIANT_BASE, dummy, 0, &pl->ki) != 0) { set_error("kernel attribute query failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(KSPEC_ERR_CUDA); }
         if (pl->ki.ctasPerSm < 1) { set_error("fused kernel for fftSize %d does not fit on this device", fftSize); return fail(KSPEC_ERR_UNSUPPORTED); }
     } else {
         char err[256] = "";
@@ -334,8 +342,9 @@ int kspec_plan_info(const kspec_plan* pl, kspec_plan_info_t* info) {
     memset(info, 0, sizeof(*info));
     info->fft_size = pl->F; info->full_size = pl->S; info->n_frames = (int)pl->offs.size(); info->precision = pl->prec;
     info->path = pl->path; info->in_fmt = pl->inFmt; info->device = pl->device; info->sm_count = pl->smCount;
-    info->cta_threads = pl->ki.ctaThreads; info->ctas_per_sm = pl->ki.ctasPerSm; info->smem_bytes = pl->ki.smemBytes;
-    info->scans_per_cta = pl->ki.teams; info->tma_stages = pl->ki.stages; info->conv_size = pl->convSize; info->win_adj = pl->winAdj;
+    const SmemKernelInfo& ki = pl->kiMulti.ctasPerSm > 0 ? pl->kiMulti : pl->ki;     // what a large batch runs
+    info->cta_threads = ki.ctaThreads; info->ctas_per_sm = ki.ctasPerSm; info->smem_bytes = ki.smemBytes;
+    info->scans_per_cta = ki.teams; info->tma_stages = ki.stages; info->conv_size = pl->convSize; info->win_adj = pl->winAdj;
     return KSPEC_OK;
 }
 

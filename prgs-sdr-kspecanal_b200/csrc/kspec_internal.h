@@ -43,13 +43,15 @@ struct ScanParams {
 struct SmemKernelInfo { int ctaThreads, smemBytes, teams, ctasPerSm, stages; };
 
 // one per (precision, ingest format); defined in smem_inst_*.cu.  info != nullptr: query only, no launch.
-int launch_smem_f32_u8(int log2F, const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info);
-int launch_smem_f32_c64(int log2F, const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info);
-int launch_smem_f32_c128(int log2F, const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info);
-int launch_smem_f64_u8(int log2F, const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info);
-int launch_smem_f64_c64(int log2F, const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info);
-int launch_smem_f64_c128(int log2F, const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info);
+// variant: SMEM_VARIANT_BASE, or SMEM_VARIANT_MULTI (fftSize 2048, float32: four independent teams per CTA, for large batches)
+int launch_smem_f32_u8(int log2F, int variant, const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info);
+int launch_smem_f32_c64(int log2F, int variant, const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info);
+int launch_smem_f32_c128(int log2F, int variant, const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info);
+int launch_smem_f64_u8(int log2F, int variant, const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info);
+int launch_smem_f64_c64(int log2F, int variant, const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info);
+int launch_smem_f64_c128(int log2F, int variant, const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info);
 
+constexpr int SMEM_VARIANT_BASE = 0, SMEM_VARIANT_MULTI = 1;
 constexpr int SMEM_MAX_LOG2F_F32 = 14;
 constexpr int SMEM_MAX_LOG2F_F64 = 13;
 constexpr int SMEM_MIN_LOG2F = 4;

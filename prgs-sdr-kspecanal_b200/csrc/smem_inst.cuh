@@ -6,18 +6,28 @@
 
 namespace kspec {
 
-int KSPEC_INST_NAME(int log2F, const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info) {
+int KSPEC_INST_NAME(int log2F, int variant, const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info) {
+    constexpr bool F32 = sizeof(KSPEC_INST_T) == 4;
+    if constexpr (F32) {
+        if (log2F == 11) {
+            // the headline shape (fftSize 2048, float32): tuned layouts, see profiles/README.md
+            int var = variant == SMEM_VARIANT_MULTI ? 4 : 3;
 #ifdef KSPEC_INST_VARIANTS
-    // tuning experiments on the headline shape only (fftSize 2048): KSPEC_VARIANT=1..3 in the environment
-    if (log2F == 11) {
-        static const int var = [] { const char* e = getenv("KSPEC_VARIANT"); return e ? atoi(e) : 0; }();
-        if (var == 1) return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, 11, 1>(p, grid, st, info);
-        if (var == 2) return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, 11, 2>(p, grid, st, info);
-        if (var == 3) return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, 11, 3>(p, grid, st, info);
-    }
+            static const int forced = [] { const char* e = getenv("KSPEC_VARIANT"); return e ? atoi(e) : -1; }();
+            if (forced >= 0) { if (variant == SMEM_VARIANT_MULTI) return (int)cudaErrorInvalidValue; var = forced; }
+            if (var == 0) return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, 11, 0>(p, grid, st, info);
+            if (var == 1) return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, 11, 1>(p, grid, st, info);
+            if (var == 2) return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, 11, 2>(p, grid, st, info);
+            if (var == 5) return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, 11, 5>(p, grid, st, info);
+            if (var == 6) return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, 11, 6>(p, grid, st, info);
 #endif
+            if (var == 4) return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, 11, 4>(p, grid, st, info);
+            return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, 11, 3>(p, grid, st, info);
+        }
+    }
+    if (variant != SMEM_VARIANT_BASE) return (int)cudaErrorInvalidValue;
     switch (log2F) {
-#define KSPEC_CASE(L) case L: if constexpr (L <= KSPEC_INST_MAXLOG2F) return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, L>(p, grid, st, info); else break;
+#define KSPEC_CASE(L) case L: if constexpr (L <= KSPEC_INST_MAXLOG2F && !(F32 && L == 11)) return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, L>(p, grid, st, info); else break;
         KSPEC_CASE(4) KSPEC_CASE(5) KSPEC_CASE(6) KSPEC_CASE(7) KSPEC_CASE(8) KSPEC_CASE(9) KSPEC_CASE(10)
         KSPEC_CASE(11) KSPEC_CASE(12) KSPEC_CASE(13) KSPEC_CASE(14)
 #undef KSPEC_CASE
