@@ -107,6 +107,13 @@ int kspec_zerospan_batch(kspec_plan* plan, const void* samples, int64_t nScans, 
                          double* max, double* min, double* avg, int carry,
                          int64_t scanIndexBase, int64_t nScansTotal);
 
+/* ---- zero_span loop body when the per-scan spectra already exist: zeroSpanPlay (K:547-564 feeding K:469-484) ------
+ * lin_rows: nScans x fftSize float64, linear and shifted -- what sdr_curscan returns and zero_span_save pickled.
+ * db_rows / hm_rows may be NULL; max/min/avg/carry as in kspec_zerospan_batch. */
+int kspec_zerospan_rows_batch(kspec_plan* plan, const double* lin_rows, int64_t nScans, double gain, const double* adj,
+                              int hmMode, int xRes, double* db_rows, double* hm_rows,
+                              double* max, double* min, double* avg, int carry);
+
 /* ---- _scan_range step loop (K:619-668) for one full pass --------------------------------------------------------
  * samples: nSteps*fullSize elements, step i = capture taken after tuning to startFreq + fS/2 + i*fS*R.
  * stepOk[i]==0: tune failed, the reference substitutes ones(fftSize) (K:635-639); may be NULL (all ok).

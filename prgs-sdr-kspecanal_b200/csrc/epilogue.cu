@@ -15,17 +15,34 @@ namespace {
 
 __device__ __forceinline__ double d_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
 
+// block = (32 bins) x (FIN_Y slot groups): the per-team partials are reduced by FIN_Y threads per bin in parallel
+// (a batch of the headline shape leaves 592 partials), then the y == 0 thread finishes the bin.
+constexpr int FIN_Y = 16;
 template <typename T>
 __global__ void stats_finish_kernel(const T* __restrict__ wsMax, const T* __restrict__ wsMin, int slots,
                                     const T* __restrict__ avgRows, int avgWin, int F, const double* __restrict__ carry,
                                     int firstIsSeed, double avgScale, double* __restrict__ out) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= F) return;
-    double mx = carry ? carry[j] : -d_inf();
-    double mn = carry ? carry[F + j] : d_inf();
-    for (int s = 0; s < slots; ++s) {
-        mx = fmax(mx, (double)wsMax[(int64_t)s * F + j]);
-        mn = fmin(mn, (double)wsMin[(int64_t)s * F + j]);
+    __shared__ double shMax[FIN_Y][33], shMin[FIN_Y][33];
+    const int j = blockIdx.x * 32 + threadIdx.x;
+    const bool inb = j < F;
+    double mx = -d_inf(), mn = d_inf();
+    if (inb) {
+        for (int s = threadIdx.y; s < slots; s += FIN_Y) {
+            mx = fmax(mx, (double)wsMax[(int64_t)s * F + j]);
+            mn = fmin(mn, (double)wsMin[(int64_t)s * F + j]);
+        }
+    }
+    shMax[threadIdx.y][threadIdx.x] = mx;
+    shMin[threadIdx.y][threadIdx.x] = mn;
+    __syncthreads();
+    if (threadIdx.y != 0 || !inb) return;
+    for (int y = 1; y < FIN_Y; ++y) {
+        mx = fmax(mx, shMax[y][threadIdx.x]);
+        mn = fmin(mn, shMin[y][threadIdx.x]);
+    }
+    if (carry) {
+        mx = fmax(mx, carry[j]);
+        mn = fmin(mn, carry[F + j]);
     }
     double a;
     int r = 0;
@@ -113,7 +130,7 @@ __global__ void linear_epilogue_kernel(const ScanParams p, const T* __restrict__
     if (j >= F) return;
     // np.fft.fftshift (K:396) rolls by F//2:  out = concat(in[ceil(F/2):], in[:ceil(F/2)])  ->  out[j] = in[(j + ceil(F/2)) mod F]
     const int c2 = (F + 1) / 2;
-    const int srcBin = (j + c2) % F;
+    const int srcBin = p.accShifted ? j : (j + c2) % F;
     const int src = p.accL1 ? (((srcBin & ((1 << p.accL1) - 1)) << p.accL2) + (srcBin >> p.accL1)) : srcBin;
     T* rows = reinterpret_cast<T*>(p.rows);
     T mx = 0, mn = 0;
@@ -152,7 +169,7 @@ __global__ void linear_hm_kernel(const ScanParams p, const T* __restrict__ acc, 
     T r = (mode == KSPEC_COMPRESS_MAX) ? -inf : (mode == KSPEC_COMPRESS_MIN ? inf : (T)0);
     for (int q = threadIdx.x; q < g; q += blockDim.x) {
         const int j = w * g + q;
-        const int srcBin = (j + c2) % F;
+        const int srcBin = p.accShifted ? j : (j + c2) % F;
         const int src = p.accL1 ? (((srcBin & ((1 << p.accL1) - 1)) << p.accL2) + (srcBin >> p.accL1)) : srcBin;
         T lin = acc[s * F + src] * (T)p.linScale;
         if (p.dbClip) lin = fmax(lin, (T)p.minAmp);
@@ -184,10 +201,10 @@ inline int nblk(int64_t n, int t) { return (int)((n + t - 1) / t); }
 void launch_stats_finish(int prec, const void* wsMax, const void* wsMin, int slots, const void* avgRows, int avgWin, int F,
                          const double* carry, int firstIsSeed, double avgScale, double* out, cudaStream_t st) {
     if (prec == KSPEC_PREC_F32)
-        stats_finish_kernel<float><<<nblk(F, 128), 128, 0, st>>>((const float*)wsMax, (const float*)wsMin, slots,
+        stats_finish_kernel<float><<<nblk(F, 32), dim3(32, FIN_Y), 0, st>>>((const float*)wsMax, (const float*)wsMin, slots,
                                                                  (const float*)avgRows, avgWin, F, carry, firstIsSeed, avgScale, out);
     else
-        stats_finish_kernel<double><<<nblk(F, 128), 128, 0, st>>>((const double*)wsMax, (const double*)wsMin, slots,
+        stats_finish_kernel<double><<<nblk(F, 32), dim3(32, FIN_Y), 0, st>>>((const double*)wsMax, (const double*)wsMin, slots,
                                                                   (const double*)avgRows, avgWin, F, carry, firstIsSeed, avgScale, out);
 }
 

@@ -403,6 +403,56 @@ int kspec_zerospan_batch_dev(kspec_plan* pl, const void* dSamples, int64_t nScan
     return KSPEC_OK;
 }
 
+// zero_span loop body on spectra that already exist (zeroSpanPlay): dB, Max/Min/Avg, waterfall rows on the GPU
+int kspec_zerospan_rows_batch(kspec_plan* pl, const double* linRows, int64_t nScans, double gain, const double* adj, int hmMode,
+                              int xRes, double* dbRows, double* hm_rows, double* mx, double* mn, double* av, int carry) {
+    if (check_plan(pl)) return KSPEC_ERR_ARG;
+    if (!linRows || nScans < 1 || !mx || !mn || !av) { set_error("bad rows batch arguments"); return KSPEC_ERR_ARG; }
+    if (hmMode < KSPEC_COMPRESS_RAW || hmMode > KSPEC_COMPRESS_MIN) { set_error("unknown pltCompressHM %d", hmMode); return KSPEC_ERR_ARG; }
+    const int F = pl->F;
+    const int W = hm_width(F, xRes, hmMode);
+    if (hm_rows && (xRes < 1 || F % W != 0)) { set_error("fftSize %d is not a multiple of the waterfall width %d", F, W); return KSPEC_ERR_ARG; }
+    DeviceGuard guard(pl->device);
+    const size_t rb = real_bytes(pl->prec);
+    const int64_t n = nScans * F;
+    int rc;
+    if ((rc = pl->wide.reserve((size_t)n * 8)) || (rc = pl->acc.reserve((size_t)n * rb))) return rc;
+    CK(cudaMemcpyAsync(pl->wide.p, linRows, (size_t)n * 8, cudaMemcpyHostToDevice, pl->st));
+    const void* dAcc = pl->wide.p;
+    if (pl->prec == KSPEC_PREC_F32) { launch_narrow(pl->prec, (const double*)pl->wide.p, pl->acc.p, n, pl->st); pl->launches += 1; dAcc = pl->acc.p; }
+    ScanParams p{};
+    p.nScans = nScans; p.linScale = 1.0; p.gain = gain; p.accShifted = 1; p.wantStats = 1;
+    p.rowsKind = dbRows ? KSPEC_ROWS_DB : KSPEC_ROWS_NONE;
+    if (dbRows) { if ((rc = pl->rows.reserve((size_t)n * rb))) return rc; p.rows = pl->rows.p; }
+    if (hm_rows) { if ((rc = pl->hm.reserve((size_t)nScans * W * rb))) return rc; p.hm = pl->hm.p; p.hmMode = hmMode; p.hmW = W; }
+    p.avgWin = (int)(nScans < AVG_WINDOW ? nScans : AVG_WINDOW);
+    if ((rc = pl->avgRows.reserve((size_t)p.avgWin * F * rb)) || (rc = pl->wsMax.reserve((size_t)F * rb)) ||
+        (rc = pl->wsMin.reserve((size_t)F * rb)) || (rc = pl->stats.reserve((size_t)3 * F * 8)))
+        return rc;
+    p.avgRows = pl->avgRows.p; p.wsMax = pl->wsMax.p; p.wsMin = pl->wsMin.p;
+    if (adj) {
+        if ((rc = pl->adj64.reserve((size_t)F * 8)) || (rc = pl->adj.reserve((size_t)F * rb))) return rc;
+        CK(cudaMemcpyAsync(pl->adj64.p, adj, (size_t)F * 8, cudaMemcpyHostToDevice, pl->st));
+        launch_narrow(pl->prec, (const double*)pl->adj64.p, pl->adj.p, F, pl->st);
+        pl->launches += 1;
+        p.adj = pl->adj.p;
+    }
+    const double* dCarry = nullptr;
+    if (carry) {
+        if ((rc = pl->carry.reserve((size_t)3 * F * 8))) return rc;
+        CK(cudaMemcpyAsync(pl->carry.p, mx, (size_t)F * 8, cudaMemcpyHostToDevice, pl->st));
+        CK(cudaMemcpyAsync((double*)pl->carry.p + F, mn, (size_t)F * 8, cudaMemcpyHostToDevice, pl->st));
+        CK(cudaMemcpyAsync((double*)pl->carry.p + 2 * F, av, (size_t)F * 8, cudaMemcpyHostToDevice, pl->st));
+        dCarry = (const double*)pl->carry.p;
+    }
+    launch_linear_epilogue(pl->prec, p, dAcc, F, 1, pl->st);
+    launch_stats_finish(pl->prec, pl->wsMax.p, pl->wsMin.p, 1, pl->avgRows.p, p.avgWin, F, dCarry, carry ? 0 : 1, 1.0, (double*)pl->stats.p, pl->st);
+    pl->launches += hm_rows ? 3 : 2;
+    CK(cudaGetLastError());
+    pl->lastScans = nScans; pl->lastRowsKind = p.rowsKind; pl->lastW = W; pl->lastHm = hm_rows != nullptr; pl->haveBatch = true;
+    return kspec_zerospan_fetch(pl, dbRows, hm_rows, mx, mn, av);
+}
+
 int kspec_zerospan_fetch(kspec_plan* pl, double* rows, double* hm_rows, double* mx, double* mn, double* av) {
     if (check_plan(pl)) return KSPEC_ERR_ARG;
     if (!pl->haveBatch) { set_error("kspec_zerospan_fetch before any batch"); return KSPEC_ERR_STATE; }

@@ -38,6 +38,7 @@ struct ScanParams {
     void* hm;                  // device T[nScans][hmW] or null
     // linear-row engines only: accumulation rows stored [k1][k2] with bin k = k1 + 2^accL1 * k2 (0: natural order)
     int32_t accL1, accL2;
+    int32_t accShifted;        // acc rows are already fftshift-ed and normalised (zeroSpanPlay records)
 };
 
 struct SmemKernelInfo { int ctaThreads, smemBytes, teams, ctasPerSm, stages; };

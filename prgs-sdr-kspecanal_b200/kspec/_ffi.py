@@ -53,6 +53,7 @@ SIGNATURES = {
     "kspec_curscan": (C.c_int, [_P, _P, _D]),
     "kspec_zerospan_batch": (C.c_int, [_P, _P, _I64, C.c_double, _D, C.c_int, C.c_int, C.c_int, _D, _D, _D, _D, _D, C.c_int,
                                        _I64, _I64]),
+    "kspec_zerospan_rows_batch": (C.c_int, [_P, _D, _I64, C.c_double, _D, C.c_int, C.c_int, _D, _D, _D, _D, _D, C.c_int]),
     "kspec_scan_batch": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_uint8), C.POINTER(_I64), C.POINTER(_I64), _I64, C.c_double,
                                    C.c_double, C.c_int, C.c_int, _D, _D, _D, _D]),
     "kspec_plotcompress": (C.c_int, [_P, _D, _I64, C.c_int, C.c_int, _D]),

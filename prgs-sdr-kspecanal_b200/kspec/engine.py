@@ -110,6 +110,24 @@ class Plan:
                                               1 if state is not None else 0, int(scan_index_base), int(total)))
         return dict(rows=rows_out, hm_rows=hm_out, max=mx, min=mn, avg=av)
 
+    # -- zero_span loop body on existing spectra: zeroSpanPlay (K:547-564 -> K:469-484) ----------------------
+    def zerospan_rows_batch(self, lin_rows, gain, x_res, hm_mode="MAX", adj=None, want_rows=True, want_hm=True, state=None):
+        lin = np.ascontiguousarray(lin_rows, dtype=np.float64)
+        n, F = lin.shape
+        if F != self.fft_size:
+            raise ValueError("rows must have fftSize=%d bins" % self.fft_size)
+        rows_out = np.empty((n, F), dtype=np.float64) if want_rows else None
+        hm_out = np.empty((n, heatmap_width(F, x_res, hm_mode)), dtype=np.float64) if want_hm else None
+        if state is not None:
+            mx, mn, av = (np.array(s, dtype=np.float64, copy=True) for s in state)
+        else:
+            mx, mn, av = (np.empty(F, dtype=np.float64) for _ in range(3))
+        adj_a = None if adj is None else np.ascontiguousarray(adj, dtype=np.float64)
+        check(_ffi.lib().kspec_zerospan_rows_batch(self._h, dptr(lin), n, float(gain), dptr(adj_a), _ffi.COMPRESS[hm_mode.upper()],
+                                                   int(x_res), dptr(rows_out), dptr(hm_out), dptr(mx), dptr(mn), dptr(av),
+                                                   1 if state is not None else 0))
+        return dict(rows=rows_out, hm_rows=hm_out, max=mx, min=mn, avg=av)
+
     # -- _scan_range step loop (K:619-668) ---------------------------------------------------------------
     def scan_batch(self, samples, n_steps, i_start, i_done, total_entries, min_amp, gain, state, pass_index,
                    step_ok=None, base_is_raw=False):

@@ -271,6 +271,35 @@ def zero_span_play(d):
     return data
 
 
+def zero_span_play_all(d, block=64):
+    """zeroSpanPlay end to end (do_run, K:1131-1134): zero_span with sdr_curscan re-bound to zero_span_play.  Records are
+    read in blocks and the loop body (dB, Max/Min/Avg, waterfall rows, K:469-484) runs on the GPU.  Returns #scans."""
+    zero_span_play_setup(d)
+    zero_span_init(d)
+    done = 0
+    while done < d["prgLoopCnt"] and not d["cmd.stop"]:
+        recs = []
+        while len(recs) < min(block, d["prgLoopCnt"] - done):
+            r = zero_span_play(d)
+            if r is None:
+                break
+            recs.append(r)
+        if not recs:
+            break
+        state = None
+        if d.get("Fft.Max") is not None:
+            state = (d["Fft.Max"], d["Fft.Min"], d["Fft.Avg"])
+        adj = d["Fft.Adj"] if d.get("AdjSigLvls", "") != "" else None
+        out = _plan(d).zerospan_rows_batch(np.array(recs), d["gain"], d["xRes"], d["pltCompressHM"], adj=adj, state=state)
+        d["Fft.Max"], d["Fft.Min"], d["Fft.Avg"], d["Fft.Cur"] = out["max"], out["min"], out["avg"], out["rows"][-1]
+        for r in out["hm_rows"]:
+            d["fftHM"][d["fftHMIndex"], :] = r
+            d["fftHMIndex"] = (d["fftHMIndex"] + 1) % HEATMAP_ROWS
+        done += len(recs)
+    d["zeroSpanFile"].close()
+    return done
+
+
 # ------------------------------------------------------------------------------------------------------
 # stepped scan (K:569-732)
 # ------------------------------------------------------------------------------------------------------

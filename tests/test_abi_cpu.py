@@ -83,6 +83,21 @@ def test_derive_config_matches_reference_handle_args():
         assert d["fullSize"] == row["fullSize"] and d["xRes"] == row["xRes"], a
 
 
+def test_cli_handle_args_matches_reference_table():
+    """kspec.cli.handle_args == the reference's handle_args (K:778-949) on the golden argv table"""
+    from kspec import cli
+    rows = json.load(open(os.path.join(GOLDEN, "g7_handle_args.json")))
+    for row in rows:
+        if row["fftSize"] > 2 ** 20:
+            continue
+        d = {"cmd.stop": False}
+        cli.handle_args(d, row["argv"])
+        for k in ("prgMode", "fftSize", "fullSize", "xRes", "startFreq", "endFreq", "centerFreq", "pltCompress"):
+            assert d[k] == row[k], (row["argv"], k, d[k], row[k])
+    with pytest.raises(SystemExit):
+        cli.handle_args({"cmd.stop": False}, ["zeroSpan", "noSuchKey", "1"])
+
+
 def test_scan_geometry_matches_oracle():
     from oracle import kspec_oracle as O
     for (s, e, F, R) in ((30e6, 30e6 + 11 * 2.4e6, 64, 1.0), (88e6, 109.6e6, 4096, 0.5), (100e6, 107.2e6, 1200, 0.25)):

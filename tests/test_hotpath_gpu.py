@@ -89,6 +89,25 @@ def test_zero_span_save_and_play_stream_format(tmp_path):
     H.close_plans(d)
 
 
+def test_zero_span_play_matches_reference_loop(tmp_path):
+    """zeroSpanSave on the GPU, then zeroSpanPlay on the GPU == the reference's zero_span on the same capture"""
+    g = load_golden("g1_zerospan_2048_hanning.npz")
+    p = g["params"]
+    path = str(tmp_path / "cap.save")
+    d = _d(fftSize=p["fftSize"], window="hanning", curScanNonOverlap=p["curScanNonOverlap"], prgLoopCnt=p["nScans"], gain=p["gain"],
+           zeroSpanSaveFile=path)
+    d["sdr"] = synth.ArrayRtlSdr(g["capture"])
+    assert H.zero_span_save(d) == p["nScans"]
+    d2 = _d(fftSize=p["fftSize"], zeroSpanPlayFile=path, prgLoopCnt=100)       # window/overlap do not matter for play
+    assert H.zero_span_play_all(d2, block=3) == p["nScans"]
+    for k, ref in (("Fft.Max", "fft_max"), ("Fft.Min", "fft_min"), ("Fft.Avg", "fft_avg")):
+        assert np.max(np.abs(d2[k] - g[ref])) < TOL, k
+    assert np.max(np.abs(d2["Fft.Cur"] - g["db_rows"][-1])) < TOL
+    assert np.max(np.abs(d2["fftHM"] - g["hm"])) < TOL
+    H.close_plans(d)
+    H.close_plans(d2)
+
+
 @pytest.mark.parametrize("name", ["g2_scan_64_r100.npz", "g2_scan_64_r050.npz"])
 def test_scan_range_with_tune_failure(name):
     g = load_golden(name)
@@ -109,6 +128,21 @@ def test_scan_range_with_tune_failure(name):
         d["fftHMIndex"] = (d["fftHMIndex"] + 1) % d["fftHMMax"]
     assert np.max(np.abs(freqs - g["freqs_all"])) == 0       # frequency axis: same float64 expressions
     H.close_plans(d)
+
+
+def test_cli_save_then_play(tmp_path):
+    from kspec import cli
+    raw = str(tmp_path / "cap.bin")
+    synth.to_u8_iq(synth.tones_noise(5 * 16384, seed=3, dtype=np.complex128)).tofile(raw)
+    save, out = str(tmp_path / "z.save"), str(tmp_path / "play.npz")
+    assert cli.main(["zeroSpanSave", "fftSize", "2048", "window", "hanning", "curScanNonOverlap", "0.5", "iqFile", raw,
+                     "zeroSpanSaveFile", save, "prgLoopCnt", "5"]) == 0
+    assert cli.main(["zeroSpanPlay", "fftSize", "2048", "zeroSpanPlayFile", save, "outFile", out]) == 0
+    z = np.load(out)
+    assert z["Fft_Max"].shape == (2048,) and int(z["nScans"]) == 5
+    assert int(np.argmax(z["Fft_Max"])) == 1024 + 256            # +300 kHz tone at 2.4 MS/s
+    assert z["fftHM"].shape == (128, 512) and np.all(z["fftHM"][5:] == 0)
+    assert cli.main(["quickFullScan", "endFreq", "40e6", "scanRangeNonOverlap", "1.0", "prgLoopCnt", "2", "outFile", out]) == 0
 
 
 def test_unknown_modes_quit_like_the_reference():
