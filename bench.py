@@ -104,6 +104,22 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows), "reasons": reasons}
 
 
+def profiled_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the fused kernel, per launch, from the committed ncu capture of this
+    very command (profiles/README.md); None when no capture is committed."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_*final*.csv")))
+    if not files:
+        return None, None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for row in csv.reader(open(files[-1])):
+        if row and row[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(row[2]) * scale.get(row[1], 1.0)
+    return (tot or None), os.path.relpath(files[-1], ROOT)
+
+
 def base_capture():
     from kspec import synth
     return synth.tones_noise(BASE_SCANS * S, seed=1)
@@ -292,7 +308,8 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "l2": "input %.2f GiB per step >> 126 MB L2, no flush needed" % (N_SCANS * S * 8 / 2 ** 30),
                        "frames_per_s": value * 1e6 * info.n_frames / S, "parallelism": "scan-range shards x%d" % world,
                        "cta_threads": info.cta_threads, "ctas_per_sm": info.ctas_per_sm, "smem_bytes": info.smem_bytes},
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": profiled_traffic()[0], "traffic_source": profiled_traffic()[1],
                          "peak_source": peak_src, "kernel": "curscan_smem_kernel<%s,C64,11>" % ("float" if plan.precision == "f32" else "double"), "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": algorithmic_bytes(N_SCANS)},
             "cpu_baseline": {"value": cpu_v, "unit": "Msamples/s", "cores": cores, "kind": "port", "single_core_value": cpu_1,
