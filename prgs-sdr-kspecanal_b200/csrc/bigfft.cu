@@ -111,12 +111,19 @@ BigFft* bigfft_create(int prec, int inFmt, int64_t F, int path, int64_t* convSiz
     BCK(cudaMalloc(&b->dWin, (size_t)F * 8));
     BCK(cudaMemcpyAsync(b->dWin, window, (size_t)F * 8, cudaMemcpyHostToDevice, st));
     const int64_t L2 = (int64_t)1 << b->l2;
-    BCK(cudaMalloc(&b->dTw2, (size_t)L2 * 16));
-    twiddle_init_kernel<<<64, 256, 0, st>>>(b->dTw2, L2);
+    {   // per-team transforms read the linearised twiddle layout (fft_core.cuh)
+        const std::vector<double> lin2 = host_lin_twiddles(b->l2);
+        BCK(cudaMalloc(&b->dTw2, lin2.size() * 8 + 16));
+        BCK(cudaMemcpyAsync(b->dTw2, lin2.data(), lin2.size() * 8, cudaMemcpyHostToDevice, st));
+        BCK(cudaStreamSynchronize(st));
+    }
     if (b->l1 > 0) {
-        const int64_t L1 = (int64_t)1 << b->l1;
-        BCK(cudaMalloc(&b->dTw1, (size_t)L1 * 16));
-        twiddle_init_kernel<<<64, 256, 0, st>>>(b->dTw1, L1);
+        {
+            const std::vector<double> lin1 = host_lin_twiddles(b->l1);
+            BCK(cudaMalloc(&b->dTw1, lin1.size() * 8 + 16));
+            BCK(cudaMemcpyAsync(b->dTw1, lin1.data(), lin1.size() * 8, cudaMemcpyHostToDevice, st));
+            BCK(cudaStreamSynchronize(st));
+        }
         BCK(cudaMalloc(&b->dTwM, (size_t)M * 16));
         twiddle_init_kernel<<<1024, 256, 0, st>>>(b->dTwM, M);
         BCK(cudaMalloc(&b->dZ, (size_t)M * 16));

@@ -160,10 +160,10 @@ curscan_smem_kernel(const ScanParams p) {
         else __syncthreads();
         (void)team;
     };
-    const cx<T>* twtab = gtw;
+    const cx<T>* twtab = reinterpret_cast<const cx<T>*>(p.twLin);      // linearised table (fft_core.cuh), global
     if constexpr (C::TWSMEM) {
         cx<T>* stw = reinterpret_cast<cx<T>*>(smem_raw + SC::TW_OFS);
-        build_lin_twiddles<T, LOG2F, LOG2P>(stw, gtw, threadIdx.x, C::CTA);
+        for (int i = threadIdx.x; i < F - (1 << L0); i += C::CTA) stw[i] = twtab[i];
         twtab = stw;
     }
 

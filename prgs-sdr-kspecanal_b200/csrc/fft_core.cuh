@@ -214,11 +214,11 @@ __device__ __forceinline__ void load_twiddles(cx<T>* dst, const cx<T>* __restric
 //            (global / L1) at every use.
 //   DBUF   : two exchange buffers (one barrier per exchange) or one (two barriers).
 // `sync` is a functor: team-wide barrier.
-// Twiddle sources for the stages >= 1 when they are not register resident:
-//   TWLDG  = true : the natural table tw[k] = exp(-2 pi i k/F) in global memory, read through the read-only path;
-//   TWLDG  = false: a "linearised" copy in shared memory, one block per stage laid out [t-1][k], k = j mod Ns, so that
-//                   the lanes of a warp read consecutive words (the natural table would be read with stride t*F/(Ns*R):
-//                   8..16-way bank conflicts).  Block s starts at tw_lin_offset(lns_s); the total is F - R0 entries.
+// Twiddles of the stages >= 1, when they are not register resident, come from a "linearised" table: one block per stage
+// laid out [t-1][k], k = j mod Ns, holding exp(-2 pi i t k/(Ns R)), so that the lanes of a warp read consecutive words
+// (the natural table exp(-2 pi i k/F) would be read with stride t*F/(Ns*R): scattered sectors in L1, 8..16-way bank
+// conflicts in shared memory).  Block s starts at tw_lin_offset(lns_s); the total is F - R0 entries.
+//   TWLDG = true : the table is in global memory, read through the read-only path;   false: a copy in shared memory.
 template <int LOG2F, int LOG2P> __host__ __device__ constexpr int tw_lin_offset(int lns) {
     int ofs = 0, cur = stage_l<LOG2F, LOG2P>(0);
     while (cur < lns) {
@@ -244,9 +244,9 @@ __device__ __forceinline__ void build_lin_twiddles(cx<T>* dst, const cx<T>* __re
 
 template <bool LDG, int LOG2F, int LOG2P, int LNS, typename C>
 __device__ __forceinline__ C ld_tw(const C* __restrict__ table, int t, int k) {
-    constexpr int L = stage_l<LOG2F, LOG2P>(LNS);
-    if constexpr (LDG) return __ldg(&table[(t * k) << (LOG2F - LNS - L)]);
-    else return table[tw_lin_offset<LOG2F, LOG2P>(LNS) + ((t - 1) << LNS) + k];
+    const C* p = &table[tw_lin_offset<LOG2F, LOG2P>(LNS) + ((t - 1) << LNS) + k];
+    if constexpr (LDG) return __ldg(p);
+    else return *p;
 }
 
 template <typename T, int LOG2F, int LOG2P, bool TWREGS, bool DBUF, int LNS, int OFS, int XI, bool TWLDG = true, typename Sync>

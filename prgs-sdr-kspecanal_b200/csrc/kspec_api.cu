@@ -77,6 +77,7 @@ struct kspec_plan {
     int32_t* dOffs = nullptr;
     void* dWin = nullptr;
     void* dTw = nullptr;
+    void* dTwLin = nullptr;
     // grow-only workspaces
     DevBuf in, rows, hm, wsMax, wsMin, avgRows, adj, adj64, carry, stats, wide, acc, l2, misc;
     // what the last *_dev batch left behind (for fetch)
@@ -116,6 +117,7 @@ ScanParams base_params(const kspec_plan* pl, const void* dSamples, int64_t nScan
     p.nFrames = (int)pl->offs.size();
     p.win = pl->dWin;
     p.tw = pl->dTw;
+    p.twLin = pl->dTwLin;
     p.cumuMode = pl->cumu;
     p.linScale = pl->linScale;
     p.u8Offset = pl->u8off;
@@ -184,6 +186,25 @@ int hm_width(int F, int xRes, int hmMode) { return (hmMode != KSPEC_COMPRESS_RAW
 }  // namespace
 
 namespace kspec {
+std::vector<double> host_lin_twiddles(int log2F) {
+    // same schedule as fft_core.cuh: radix 2^LOG2P stages, the remainder last; block per stage >= 1 laid out [t-1][k]
+    const int log2P = log2F >= 7 ? 4 : (log2F >= 5 ? 3 : 2);
+    std::vector<double> out;
+    int lns = log2P < log2F ? log2P : log2F;
+    while (lns < log2F) {
+        const int l = (log2P < log2F - lns) ? log2P : (log2F - lns);
+        const int R = 1 << l, NS = 1 << lns;
+        for (int t = 1; t < R; ++t)
+            for (int k = 0; k < NS; ++k) {
+                // exact reduction of t*k/(NS*R) to an octant-symmetric angle is not needed at float64: |err| ~ 1e-16
+                const double a = -2.0 * M_PI * (double)t * (double)k / ((double)NS * (double)R);
+                out.push_back(cos(a));
+                out.push_back(sin(a));
+            }
+        lns += l;
+    }
+    return out;
+}
 bool plan_stats_view(kspec_plan* pl, double** stats3F, int* F, cudaStream_t* st) {
     if (!pl || !pl->haveBatch || !pl->stats.p) return false;
     *stats3F = (double*)pl->stats.p;
@@ -288,6 +309,14 @@ int kspec_plan_create(kspec_plan** out, int fftSize, int64_t fullSize, double no
         }
         if (fftSize >= 4) { tw[2 * (fftSize / 4)] = 0.0; tw[2 * (fftSize / 4) + 1] = -1.0; tw[2 * (fftSize / 2)] = -1.0; tw[2 * (fftSize / 2) + 1] = 0.0;
                             tw[2 * (3 * fftSize / 4)] = 0.0; tw[2 * (3 * fftSize / 4) + 1] = 1.0; }
+        const std::vector<double> lin = host_lin_twiddles(pl->log2F);
+        if (cudaMalloc(&pl->dTwLin, (lin.size() + 2) * rb) != cudaSuccess) { set_error("table allocation failed"); return fail(KSPEC_ERR_NOMEM); }
+        if (precision == KSPEC_PREC_F32) {
+            std::vector<float> l32(lin.begin(), lin.end());
+            cudaMemcpy(pl->dTwLin, l32.data(), l32.size() * 4, cudaMemcpyHostToDevice);
+        } else if (!lin.empty()) {
+            cudaMemcpy(pl->dTwLin, lin.data(), lin.size() * 8, cudaMemcpyHostToDevice);
+        }
         if (precision == KSPEC_PREC_F32) {
             std::vector<float> w32(fftSize), t32(2 * (size_t)fftSize);
             for (int i = 0; i < fftSize; ++i) w32[i] = (float)window[i];
@@ -322,6 +351,7 @@ int kspec_plan_destroy(kspec_plan* pl) {
     if (pl->dOffs) cudaFree(pl->dOffs);
     if (pl->dWin) cudaFree(pl->dWin);
     if (pl->dTw) cudaFree(pl->dTw);
+    if (pl->dTwLin) cudaFree(pl->dTwLin);
     for (int i = 0; i < kspec_plan::KT; ++i) { if (pl->kev[i][0]) cudaEventDestroy(pl->kev[i][0]); if (pl->kev[i][1]) cudaEventDestroy(pl->kev[i][1]); }
     if (pl->ev0) cudaEventDestroy(pl->ev0);
     if (pl->ev1) cudaEventDestroy(pl->ev1);

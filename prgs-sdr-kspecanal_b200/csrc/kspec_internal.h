@@ -17,6 +17,7 @@ struct ScanParams {
     int32_t nFrames;
     const void* win;           // device T[F]
     const void* tw;            // device cx<T>[F], exp(-2 pi i k / F) rounded from float64
+    const void* twLin;         // device cx<T>[F - R0], the same factors in the per-stage linearised layout (fft_core.cuh)
     int32_t cumuMode;
     double linScale;           // 2 * winAdj / F  (K:391)
     double u8Offset, u8Scale;
@@ -87,6 +88,9 @@ int bigfft_run(BigFft*, const void* samples, int64_t scanStride, int64_t nScans,
 
 int bigfft_acc_l1(const BigFft*);
 int bigfft_acc_l2(const BigFft*);
+
+// float64 (re, im) pairs of the linearised twiddle table of an F = 2^log2F transform with the kernels' stage schedule
+std::vector<double> host_lin_twiddles(int log2F);
 
 void set_error(const char* fmt, ...);
 
