@@ -128,9 +128,18 @@ int kspec_scan_batch(kspec_plan* plan, const void* samples, int nSteps, const ui
 /* ---- _data_plotcompress (K:168-202) on a float64 vector -------------------------------------------------------- */
 int kspec_plotcompress(kspec_plan* plan, const double* y, int64_t n, int xRes, int mode, double* out);
 
+/* ---- SURVEY 8f "next" rows -------------------------------------------------------------------------------------------
+ * plot_highs (K:243-272): indices of the numMarkers (<= 64) strongest points of a level curve that are at least
+ * delta4Marking*(freqs[n-1]-freqs[0]) apart, strongest first; the weakest point is never marked (K:254). */
+int kspec_plot_highs(kspec_plan* plan, const double* freqs, const double* levels, int64_t n, int numMarkers,
+                     double delta4Marking, int64_t* idxOut, int* nOut);
+/* data_proc 'Conv' / pltCompress conv (K:113-120): np.convolve(vals, taps, 'same'), then the first and last `edge`
+ * (12 in the reference) points are set to the mean of the result.  taps = np.kaiser(128, 64) in the reference (K:87). */
+int kspec_conv_smooth(kspec_plan* plan, const double* vals, int64_t n, const double* taps, int nTaps, int edge, double* out);
+
 /* ---- device-resident variants (zero-copy pipelines; what bench.py times for the roofline) ---------------------
- * kspec_dev_* manage device buffers on the plan's device (kspec_dev_alloc adds the 16-byte tail padding the staged
- * bulk copies need; sample buffers from other allocators must provide it themselves); kspec_zerospan_batch_dev consumes samples already in HBM
+ * kspec_dev_* manage device buffers on the plan's device (sample buffers must be 16-byte aligned, which every CUDA
+ * allocation is); kspec_zerospan_batch_dev consumes samples already in HBM
  * and leaves rows / hm rows / stats in plan-owned device buffers until kspec_zerospan_fetch copies them out.
  * kspec_timer_* bracket work on the plan's stream with CUDA events. */
 int kspec_dev_alloc(kspec_plan* plan, int64_t bytes, void** dptr);

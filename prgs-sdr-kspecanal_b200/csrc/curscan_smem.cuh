@@ -74,8 +74,8 @@ template <typename T> struct Ingest<T, KSPEC_IN_C128> {
 // The raw samples of the NEXT frame(s) are fetched by one elected thread with cp.async.bulk (global -> shared,
 // completion on an mbarrier) while the CTA transforms the current frame, so the first FFT stage reads its operands
 // from shared memory and never waits on HBM/L2 latency.  A bulk copy needs 16-byte aligned addresses and sizes; frame
-// offsets int(i*F*r) (K:386) can be odd, so the copy starts at the offset rounded down to 16 bytes and carries
-// SLACK extra elements; device sample buffers therefore need 16 bytes of tail padding (kspec_dev_alloc adds it).
+// offsets int(i*F*r) (K:386) can be odd, so a copy covers the 16-byte granules around its frame (at most SLACK extra
+// elements) and is clipped at the end of the batch: nothing outside the caller's samples is ever read.
 template <typename T, int INFMT, int LOG2F, int VAR = 0> struct StageCfg {
     using C = SmemCfg<T, LOG2F, VAR>;
     static constexpr int EB = Ingest<T, INFMT>::ELEM_BYTES;
@@ -191,9 +191,15 @@ curscan_smem_kernel(const ScanParams p) {
         int64_t sc = it * scansPerIter + slot;
         if (sc >= p.nScans) sc = p.nScans - 1;
         const int64_t e0 = sc * p.scanStride + p.frameOffs[f];
-        const int64_t e0a = (SC::SLACK > 0) ? (e0 & ~(int64_t)(SC::SLACK - 1)) : e0;
+        // 16-byte granules covering [e0, e0+F), never past the end of the batch (the batch length is a whole number of
+        // granules whenever fullSize is, which holds for every fullSize the reference can produce, K:926-929)
+        constexpr int64_t GM = SC::SLACK > 0 ? SC::SLACK - 1 : 0;
+        const int64_t e0a = e0 & ~GM;
+        int64_t e1a = (e0 + F + GM) & ~GM;
+        const int64_t total = (p.nScans * p.scanStride + GM) & ~GM;
+        if (e1a > total) e1a = total;
         const int s = (STG == 2) ? (int)(g & 1) : 0;
-        constexpr uint32_t bytes = (uint32_t)((F + SC::SLACK) * SC::EB);
+        const uint32_t bytes = (uint32_t)((e1a - e0a) * SC::EB);
         mbar_expect_tx(&mbar[s], bytes);
         tma_load_1d(stage0 + s * SC::STAGE_BYTES, reinterpret_cast<const unsigned char*>(p.samples) + e0a * SC::EB, bytes, &mbar[s]);
     };

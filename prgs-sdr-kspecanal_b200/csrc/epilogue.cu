@@ -194,6 +194,85 @@ __global__ void linear_hm_kernel(const ScanParams p, const T* __restrict__ acc, 
     }
 }
 
+// plot_highs (K:243-272): walk the points by descending level; mark a point unless an already marked one lies closer
+// than delta in x; stop after numMarkers.  One block: numMarkers rounds of a block-wide arg-max over the still
+// admissible points (equal levels: lowest index first; the reference's unstable argsort leaves that order open).
+__global__ void plot_highs_kernel(const double* __restrict__ x, const double* __restrict__ y, int64_t n, int numMarkers, double delta,
+                                  int64_t* __restrict__ idxOut, int* __restrict__ nOut) {
+    __shared__ double shV[1024];
+    __shared__ long long shI[1024];
+    __shared__ double marked[64];
+    __shared__ long long markedIdx[64];
+    __shared__ int nMarked;
+    __shared__ long long lowest;
+    if (threadIdx.x == 0) nMarked = 0;
+    // the reference's loop np.arange(-1, -len, -1) never reaches the smallest element: find it once and skip it
+    double bv = d_inf();
+    long long bi = -1;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x)
+        if (y[i] < bv) { bv = y[i]; bi = i; }
+    shV[threadIdx.x] = bv; shI[threadIdx.x] = bi;
+    __syncthreads();
+    for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+            const double a = shV[threadIdx.x + s]; const long long ai = shI[threadIdx.x + s];
+            if (ai >= 0 && (shI[threadIdx.x] < 0 || a < shV[threadIdx.x] || (a == shV[threadIdx.x] && ai < shI[threadIdx.x]))) { shV[threadIdx.x] = a; shI[threadIdx.x] = ai; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) lowest = shI[0];
+    __syncthreads();
+    for (int m = 0; m < numMarkers; ++m) {
+        const int nm = nMarked;
+        bv = -d_inf(); bi = -1;
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+            if (i == lowest) continue;
+            const double xi = x[i];
+            bool ok = true;
+            for (int k = 0; k < nm; ++k) ok = ok && !(fabs(marked[k] - xi) < delta) && markedIdx[k] != i;   // each point is visited once
+            if (ok && (bi < 0 || y[i] > bv)) { bv = y[i]; bi = i; }
+        }
+        shV[threadIdx.x] = bv; shI[threadIdx.x] = bi;
+        __syncthreads();
+        for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+            if ((int)threadIdx.x < s) {
+                const double a = shV[threadIdx.x + s]; const long long ai = shI[threadIdx.x + s];
+                if (ai >= 0 && (shI[threadIdx.x] < 0 || a > shV[threadIdx.x] || (a == shV[threadIdx.x] && ai < shI[threadIdx.x]))) { shV[threadIdx.x] = a; shI[threadIdx.x] = ai; }
+            }
+            __syncthreads();
+        }
+        if (shI[0] < 0) break;                     // nothing admissible left (uniform: every thread reads the same slot)
+        if (threadIdx.x == 0) { idxOut[nm] = shI[0]; marked[nm] = x[shI[0]]; markedIdx[nm] = shI[0]; nMarked = nm + 1; }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *nOut = nMarked;
+}
+
+// data_proc 'Conv' (K:113-120): np.convolve(vals, taps, 'same') then the first/last 12 points := mean of the result
+__global__ void conv_same_kernel(const double* __restrict__ v, int64_t n, const double* __restrict__ taps, int m, double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t j = i + (m - 1) / 2;            // index into the full convolution
+    double acc = 0.0;
+    for (int k = 0; k < m; ++k) {
+        const int64_t a = j - k;
+        if (a >= 0 && a < n) acc += v[a] * taps[k];
+    }
+    out[i] = acc;
+}
+__global__ void conv_edges_kernel(double* __restrict__ out, int64_t n, int edge) {
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += out[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int st = blockDim.x >> 1; st > 0; st >>= 1) { if ((int)threadIdx.x < st) sh[threadIdx.x] += sh[threadIdx.x + st]; __syncthreads(); }
+    const double avg = sh[0] / (double)n;
+    __syncthreads();
+    for (int i = threadIdx.x; i < edge && i < n; i += blockDim.x) { out[i] = avg; out[n - 1 - i] = avg; }
+}
+
 inline int nblk(int64_t n, int t) { return (int)((n + t - 1) / t); }
 
 }  // namespace
@@ -231,6 +310,15 @@ void launch_scan_stitch(int prec, const void* dbRows, const uint8_t* stepOk, con
     else
         scan_stitch_kernel<double><<<nblk(total, 256), 256, 0, st>>>((const double*)dbRows, stepOk, iStart, iDone, nSteps, F,
                                                                      total, failValue, baseIsRaw, passIndex, cur, mx, mn, av);
+}
+
+void launch_plot_highs(const double* x, const double* y, int64_t n, int numMarkers, double delta, int64_t* idxOut, int* nOut, cudaStream_t st) {
+    plot_highs_kernel<<<1, 1024, 0, st>>>(x, y, n, numMarkers, delta, idxOut, nOut);
+}
+
+void launch_conv_same(const double* v, int64_t n, const double* taps, int m, int edge, double* out, cudaStream_t st) {
+    conv_same_kernel<<<nblk(n, 256), 256, 0, st>>>(v, n, taps, m, out);
+    conv_edges_kernel<<<1, 256, 0, st>>>(out, n, edge);
 }
 
 void launch_plotcompress(const double* y, int64_t n, int xRes, int mode, double* out, cudaStream_t st) {

@@ -637,6 +637,49 @@ int kspec_plotcompress(kspec_plan* pl, const double* y, int64_t n, int xRes, int
     return KSPEC_OK;
 }
 
+// ---- "next" rows of SURVEY 8f: plot_highs peak picking and the Conv display mode ----------------------------------------
+int kspec_plot_highs(kspec_plan* pl, const double* freqs, const double* levels, int64_t n, int numMarkers, double delta4Marking,
+                     int64_t* idxOut, int* nOut) {
+    if (check_plan(pl)) return KSPEC_ERR_ARG;
+    if (!freqs || !levels || !idxOut || !nOut || n < 1 || numMarkers < 0 || numMarkers > 64) { set_error("bad plot_highs arguments (numMarkers <= 64)"); return KSPEC_ERR_ARG; }
+    DeviceGuard guard(pl->device);
+    int rc;
+    if ((rc = pl->misc.reserve((size_t)n * 16 + 64 * 8 + 64))) return rc;
+    double* dX = (double*)pl->misc.p;
+    double* dY = dX + n;
+    int64_t* dI = (int64_t*)(dY + n);
+    int* dN = (int*)(dI + 64);
+    CK(cudaMemcpyAsync(dX, freqs, (size_t)n * 8, cudaMemcpyHostToDevice, pl->st));
+    CK(cudaMemcpyAsync(dY, levels, (size_t)n * 8, cudaMemcpyHostToDevice, pl->st));
+    const double delta = delta4Marking * (freqs[n - 1] - freqs[0]);                // K:248-249
+    launch_plot_highs(dX, dY, n, numMarkers, delta, dI, dN, pl->st);
+    pl->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(nOut, dN, sizeof(int), cudaMemcpyDeviceToHost, pl->st));
+    CK(cudaStreamSynchronize(pl->st));
+    if (*nOut > 0) CK(cudaMemcpy(idxOut, dI, (size_t)*nOut * 8, cudaMemcpyDeviceToHost));
+    return KSPEC_OK;
+}
+
+int kspec_conv_smooth(kspec_plan* pl, const double* vals, int64_t n, const double* taps, int nTaps, int edge, double* out) {
+    if (check_plan(pl)) return KSPEC_ERR_ARG;
+    if (!vals || !taps || !out || n < 1 || nTaps < 1 || n < nTaps || edge < 0) { set_error("bad conv arguments (needs n >= nTaps)"); return KSPEC_ERR_ARG; }
+    DeviceGuard guard(pl->device);
+    int rc;
+    if ((rc = pl->misc.reserve((size_t)(2 * n + nTaps) * 8))) return rc;
+    double* dV = (double*)pl->misc.p;
+    double* dO = dV + n;
+    double* dT = dO + n;
+    CK(cudaMemcpyAsync(dV, vals, (size_t)n * 8, cudaMemcpyHostToDevice, pl->st));
+    CK(cudaMemcpyAsync(dT, taps, (size_t)nTaps * 8, cudaMemcpyHostToDevice, pl->st));
+    launch_conv_same(dV, n, dT, nTaps, edge, dO, pl->st);
+    pl->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, dO, (size_t)n * 8, cudaMemcpyDeviceToHost, pl->st));
+    CK(cudaStreamSynchronize(pl->st));
+    return KSPEC_OK;
+}
+
 // ---- device buffers, pinned memory, timers -----------------------------------------------------------------------
 int kspec_dev_alloc(kspec_plan* pl, int64_t bytes, void** dptr) {
     if (check_plan(pl) || !dptr || bytes < 1) { set_error("bad argument"); return KSPEC_ERR_ARG; }

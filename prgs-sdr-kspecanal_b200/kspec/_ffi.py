@@ -57,6 +57,8 @@ SIGNATURES = {
     "kspec_scan_batch": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_uint8), C.POINTER(_I64), C.POINTER(_I64), _I64, C.c_double,
                                    C.c_double, C.c_int, C.c_int, _D, _D, _D, _D]),
     "kspec_plotcompress": (C.c_int, [_P, _D, _I64, C.c_int, C.c_int, _D]),
+    "kspec_plot_highs": (C.c_int, [_P, _D, _D, _I64, C.c_int, C.c_double, C.POINTER(_I64), C.POINTER(C.c_int)]),
+    "kspec_conv_smooth": (C.c_int, [_P, _D, _I64, _D, C.c_int, C.c_int, _D]),
     "kspec_dev_alloc": (C.c_int, [_P, _I64, C.POINTER(_P)]),
     "kspec_dev_free": (C.c_int, [_P, _P]),
     "kspec_dev_upload": (C.c_int, [_P, _P, _P, _I64]),

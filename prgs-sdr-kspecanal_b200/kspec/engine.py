@@ -156,6 +156,23 @@ class Plan:
         check(_ffi.lib().kspec_plotcompress(self._h, dptr(y), len(y), int(x_res), _ffi.COMPRESS[mode], dptr(out)))
         return out
 
+    # -- plot_highs peak picking (K:243-272) and the Conv display mode (K:113-120) ------------------------------
+    def plot_highs(self, freqs, levels, num_markers=5, delta4marking=0.025):
+        x = np.ascontiguousarray(freqs, dtype=np.float64)
+        y = np.ascontiguousarray(levels, dtype=np.float64)
+        idx = np.zeros(64, dtype=np.int64)
+        n = C.c_int(0)
+        check(_ffi.lib().kspec_plot_highs(self._h, dptr(x), dptr(y), len(x), int(num_markers), float(delta4marking),
+                                          idx.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(n)))
+        return idx[:n.value].copy()
+
+    def conv_smooth(self, vals, taps, edge=12):
+        v = np.ascontiguousarray(vals, dtype=np.float64)
+        t = np.ascontiguousarray(taps, dtype=np.float64)
+        out = np.empty_like(v)
+        check(_ffi.lib().kspec_conv_smooth(self._h, dptr(v), len(v), dptr(t), len(t), int(edge), dptr(out)))
+        return out
+
     # -- device-resident pipeline (bench / zero-copy callers) -----------------------------------------------
     def dev_alloc(self, n_bytes):
         p = C.c_void_p()

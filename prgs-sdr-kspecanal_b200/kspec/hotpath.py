@@ -390,11 +390,26 @@ def _data_plotcompress(d, data, mode):
     mode = str(mode).upper()
     if mode == PLTCOMPRESS_RAW:
         return data
+    if mode == "CONV":                                   # PLTCOMPRESS_CONV -> data_proc 'Conv' (K:113-120, K:183-184)
+        return _plan(d).conv_smooth(data, DataProcConv)
     if mode in (PLTCOMPRESS_MAX, PLTCOMPRESS_AVG):
         if len(data) // d["xRes"] == 0:
             return data
         return _plan(d).plotcompress(data, d["xRes"], mode)
     prg_quit(d, "ERROR:_data_plotcompress: Unknown mode [{}]".format(mode))
+
+
+DataProcConv = np.kaiser(128, 64)                        # K:87
+
+
+def plot_highs(d, freqs, levels):
+    """K:243-272 without the matplotlib calls: the strongest points, at least pltHighsDelta4Marking of the span apart.
+    Returns [(freq, level), ...] strongest first and prints them like the reference does."""
+    idx = _plan(d).plot_highs(freqs, levels, d.get("pltHighsNumMarkers", 5), d.get("pltHighsDelta4Marking", 0.025))
+    marks = [(float(freqs[i]), float(levels[i])) for i in idx]
+    for f, lv in marks:
+        print("plotHighs:Marked: {}, {}".format(f, lv))
+    return marks
 
 
 def data_plotcompress(d, xData, yData, mode=None):
@@ -403,6 +418,8 @@ def data_plotcompress(d, xData, yData, mode=None):
         mode = d["pltCompress"]
     if str(mode).upper() == PLTCOMPRESS_RAW:
         return xData, yData
+    if str(mode).upper() == "CONV":
+        return xData, _data_plotcompress(d, yData, mode)
     return _data_plotcompress(d, xData, PLTCOMPRESS_AVG), _data_plotcompress(d, yData, mode)
 
 

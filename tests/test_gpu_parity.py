@@ -335,6 +335,38 @@ def test_plotcompress(mode):
     assert np.allclose(got, O.plotcompress(y, 512, mode), rtol=0, atol=1e-12)
 
 
+def _plot_highs_ref(freqs, levels, num, delta_frac):
+    """the marking loop of plot_highs (K:246-265) without the matplotlib calls"""
+    delta = delta_frac * (freqs[-1] - freqs[0])
+    order = levels.argsort()
+    marked, out = [], []
+    for i in np.arange(-1, -len(freqs), -1):
+        f = freqs[order[i]]
+        if not any(abs(m - f) < delta for m in marked):
+            marked.append(f)
+            out.append(int(order[i]))
+            if len(out) >= num:
+                break
+    return out
+
+
+def test_plot_highs_and_conv_display_mode():
+    rng = np.random.default_rng(3)
+    freqs = np.linspace(88e6, 108e6, 512)
+    levels = rng.normal(size=512) * 3 - 60
+    levels[[40, 41, 43, 300, 301, 480]] += 40 + np.arange(6)           # clustered peaks: the spacing rule must skip neighbours
+    with Plan(64, 512, 0.5, np.ones(64)) as plan:
+        for num, frac in ((5, 0.025), (12, 0.01), (3, 0.2), (64, 0.0)):
+            assert plan.plot_highs(freqs, levels, num, frac).tolist() == _plot_highs_ref(freqs, levels, num, frac)
+        taps = np.kaiser(128, 64)                                      # DataProcConv, K:87
+        got = plan.conv_smooth(levels, taps)
+    ref = np.convolve(levels, taps, mode="same")                       # K:113-120
+    avg = np.average(ref)
+    ref[:12] = avg
+    ref[-12:] = avg
+    assert np.max(np.abs(got - ref)) < 1e-9
+
+
 def test_known_answer_tone_every_window():
     """SURVEY section 4 KAT: bin-centred tone of amplitude A -> 2A linear (10log10(2A)-gain dB) at bin F/2+k"""
     F, k, A = 2048, 300, 0.25
