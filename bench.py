@@ -265,6 +265,8 @@ def run_ours(args):
     plan.timer_start()
     for _ in range(args.steps):
         step_dev()
+    if comm is not None:
+        comm.join(plan)              # the last exchange is inside the timed region
     ms = plan.timer_stop()
     barrier()
     launches = plan.launch_count() - l0

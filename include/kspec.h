@@ -168,9 +168,12 @@ int kspec_comm_unique_id(char id[128]);                                  /* rank
 int kspec_comm_init(kspec_comm** out, int nRanks, int rank, const char id[128], int device);
 /* MAX on max, MIN on min, SUM on avg (pre-weighted partials of kspec_zerospan_batch); n float64 each, in place */
 int kspec_comm_allreduce_stats(kspec_comm* comm, double* max, double* min, double* avg, int64_t n);
-/* same reduction directly on the statistics the plan's last kspec_zerospan_batch_dev left on the device (no host
- * round trip; enqueued on the plan's stream, read back later with kspec_zerospan_fetch) */
+/* same reduction on the statistics the plan's last kspec_zerospan_batch_dev left on the device, without a host round
+ * trip and ASYNCHRONOUSLY: the vectors are snapshotted onto the communicator's own stream and reduced there, so the
+ * plan may start its next batch at once.  kspec_comm_join makes the plan's stream wait for the reduction and copies the
+ * reduced vectors back into the plan (kspec_zerospan_fetch then returns them). */
 int kspec_comm_allreduce_plan(kspec_comm* comm, kspec_plan* plan);
+int kspec_comm_join(kspec_comm* comm, kspec_plan* plan);
 int kspec_comm_finalize(kspec_comm* comm);
 
 #ifdef __cplusplus

@@ -60,8 +60,10 @@ struct kspec_comm {
     ncclComm_t comm = nullptr;
     int device = 0, nRanks = 0, rank = 0;
     cudaStream_t st = nullptr;
+    cudaEvent_t evIn = nullptr, evCopied = nullptr, evDone = nullptr;
     double* buf = nullptr;
     size_t cap = 0;
+    int64_t pendingN = 0;      // length of the vectors of the last asynchronous plan reduction held in buf
 };
 
 #define NCK(call)                                                                         \
@@ -119,7 +121,8 @@ int kspec_comm_init(kspec_comm** out, int nRanks, int rank, const char id[128], 
     memcpy(&u, id, 128);
     ncclResult_t r = api().CommInitRank(&c->comm, nRanks, u, rank);
     if (r != ncclSuccess) { set_error("ncclCommInitRank failed: %s", api().GetErrorString(r)); delete c; return KSPEC_ERR_NCCL; }
-    if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); api().CommDestroy(c->comm); delete c; return KSPEC_ERR_CUDA; }
+    if (cudaEventCreateWithFlags(&c->evIn, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->evCopied, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->evDone, cudaEventDisableTiming) != cudaSuccess || cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); api().CommDestroy(c->comm); delete c; return KSPEC_ERR_CUDA; }
     *out = c;
     return KSPEC_OK;
 }
@@ -153,7 +156,40 @@ int kspec_comm_allreduce_plan(kspec_comm* c, kspec_plan* plan) {
     cudaStream_t st = nullptr;
     if (!plan_stats_view(plan, &stats, &F, &st)) { set_error("plan holds no batch statistics yet"); return KSPEC_ERR_STATE; }
     CCK(cudaSetDevice(c->device));
-    return comm_allreduce_device(c, stats, F, st);
+    const size_t bytes = (size_t)3 * F * 8;
+    if (c->cap < bytes) {
+        CCK(cudaStreamSynchronize(c->st));
+        if (c->buf) cudaFree(c->buf);
+        c->buf = nullptr; c->cap = 0;
+        CCK(cudaMalloc(&c->buf, bytes));
+        c->cap = bytes;
+    }
+    // snapshot the plan's statistics on the communicator's stream, release the plan's stream at once, reduce in the
+    // background: the next batch's kernels overlap the (latency-bound) NVLink exchange
+    CCK(cudaEventRecord(c->evIn, st));
+    CCK(cudaStreamWaitEvent(c->st, c->evIn, 0));
+    CCK(cudaMemcpyAsync(c->buf, stats, bytes, cudaMemcpyDeviceToDevice, c->st));
+    CCK(cudaEventRecord(c->evCopied, c->st));
+    CCK(cudaStreamWaitEvent(st, c->evCopied, 0));
+    int rc = comm_allreduce_device(c, c->buf, F, c->st);
+    if (rc) return rc;
+    CCK(cudaEventRecord(c->evDone, c->st));
+    c->pendingN = F;
+    return KSPEC_OK;
+}
+
+int kspec_comm_join(kspec_comm* c, kspec_plan* plan) {
+    if (!c || !plan) { set_error("bad join arguments"); return KSPEC_ERR_ARG; }
+    double* stats = nullptr;
+    int F = 0;
+    cudaStream_t st = nullptr;
+    if (!plan_stats_view(plan, &stats, &F, &st)) { set_error("plan holds no batch statistics yet"); return KSPEC_ERR_STATE; }
+    if (c->pendingN != F) { set_error("no reduction of this plan is pending"); return KSPEC_ERR_STATE; }
+    CCK(cudaSetDevice(c->device));
+    // the plan's stream waits for the reduction and takes the reduced vectors back: kspec_zerospan_fetch then returns them
+    CCK(cudaStreamWaitEvent(st, c->evDone, 0));
+    CCK(cudaMemcpyAsync(stats, c->buf, (size_t)3 * F * 8, cudaMemcpyDeviceToDevice, st));
+    return KSPEC_OK;
 }
 
 int kspec_comm_finalize(kspec_comm* c) {
@@ -162,6 +198,7 @@ int kspec_comm_finalize(kspec_comm* c) {
     if (c->st) cudaStreamSynchronize(c->st);
     if (c->comm && api().ok) api().CommDestroy(c->comm);
     if (c->buf) cudaFree(c->buf);
+    for (cudaEvent_t e : {c->evIn, c->evCopied, c->evDone}) if (e) cudaEventDestroy(e);
     if (c->st) cudaStreamDestroy(c->st);
     delete c;
     return KSPEC_OK;

@@ -78,6 +78,7 @@ SIGNATURES = {
     "kspec_comm_init": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_char_p, C.c_int]),
     "kspec_comm_allreduce_stats": (C.c_int, [_P, _D, _D, _D, _I64]),
     "kspec_comm_allreduce_plan": (C.c_int, [_P, _P]),
+    "kspec_comm_join": (C.c_int, [_P, _P]),
     "kspec_comm_finalize": (C.c_int, [_P]),
 }
 

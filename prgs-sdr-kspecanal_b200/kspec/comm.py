@@ -34,8 +34,13 @@ class Comm:
         check(_ffi.lib().kspec_comm_allreduce_stats(self._h, dptr(mx), dptr(mn), dptr(av), len(mx)))
 
     def allreduce_plan_stats(self, plan):
-        """in place on the statistics plan.zerospan_batch_dev left on the device (stream ordered, no host copy)"""
+        """reduce the statistics plan.zerospan_batch_dev left on the device: asynchronous, on the communicator's own
+        stream (the plan can start its next batch at once); ``join(plan)`` brings the result back into the plan"""
         check(_ffi.lib().kspec_comm_allreduce_plan(self._h, plan._h))
+
+    def join(self, plan):
+        """the plan's stream waits for the last allreduce_plan_stats and takes the reduced vectors (fetch returns them)"""
+        check(_ffi.lib().kspec_comm_join(self._h, plan._h))
 
     def close(self):
         if self._h is not None and self._h.value:

@@ -1,0 +1,76 @@
+"""Two real GPUs, one process each: scan-range shards + NCCL MAX/MIN/SUM (kspec_comm_*) == the single-GPU result.
+Skipped on boxes with one GPU (the sharding arithmetic itself is covered on CPU by tests/test_sharding_cpu.py and on one
+GPU by test_sharded_partials_combine_to_the_single_gpu_result)."""
+import os
+
+import numpy as np
+import pytest
+
+from kspec.engine import device_count
+
+pytestmark = pytest.mark.gpu
+
+F, R, GAIN, XRES, N = 256, 0.5, 19.1, 64, 48
+
+
+def _worker(rank, world, uid_path, q):
+    import time
+    import numpy as np
+    from kspec import synth
+    from kspec.comm import Comm
+    from kspec.engine import Plan
+    from kspec.sharding import shard_bounds
+    S = F * 8
+    if rank == 0:
+        uid = Comm.unique_id()
+        with open(uid_path + ".tmp", "wb") as f:
+            f.write(uid)
+        os.rename(uid_path + ".tmp", uid_path)
+    else:
+        for _ in range(600):
+            if os.path.exists(uid_path):
+                break
+            time.sleep(0.05)
+        uid = open(uid_path, "rb").read()
+    comm = Comm(world, rank, uid, rank)
+    x = synth.tones_noise(N * S, seed=77, gate=(5000, 0.5))
+    a, b = shard_bounds(N, world)[rank]
+    with Plan(F, S, R, np.hanning(F), "AVG", precision="f64", device=rank) as plan:
+        # host-vector path
+        out = plan.zerospan_batch(x[a * S:b * S], b - a, GAIN, XRES, "MAX", scan_index_base=a, n_scans_total=N)
+        comm.allreduce_host(out["max"], out["min"], out["avg"])
+        # device-resident asynchronous path
+        d = plan.dev_alloc((b - a) * S * 8)
+        plan.dev_upload(d, x[a * S:b * S])
+        plan.zerospan_batch_dev(d, b - a, GAIN, XRES, "MAX", scan_index_base=a, n_scans_total=N)
+        comm.allreduce_plan_stats(plan)
+        comm.join(plan)
+        dev = plan.zerospan_fetch()
+        plan.dev_free(d)
+    comm.close()
+    q.put((rank, out["max"], out["min"], out["avg"], dev["max"], dev["min"], dev["avg"]))
+
+
+@pytest.mark.skipif(device_count() < 2, reason="needs two GPUs")
+def test_two_gpu_shards_match_single_gpu(tmp_path):
+    import multiprocessing as mp
+    from kspec import synth
+    from kspec.engine import Plan
+    S = F * 8
+    x = synth.tones_noise(N * S, seed=77, gate=(5000, 0.5))
+    with Plan(F, S, R, np.hanning(F), "AVG", precision="f64") as plan:
+        ref = plan.zerospan_batch(x, N, GAIN, XRES, "MAX")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    uid_path = str(tmp_path / "nccl.uid")
+    procs = [ctx.Process(target=_worker, args=(r, 2, uid_path, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in res:
+        for got in (r[1:4], r[4:7]):
+            assert np.array_equal(got[0], ref["max"]) and np.array_equal(got[1], ref["min"])
+            assert np.max(np.abs(got[2] - ref["avg"])) < 1e-9
