@@ -249,6 +249,39 @@ __device__ __forceinline__ C ld_tw(const C* __restrict__ table, int t, int k) {
     else return *p;
 }
 
+// exp(-2 pi i n / 16), n = 0..15: the rotations that relate the twiddles of the butterflies of one thread in the LAST stage
+// (virtual threads j = tid + v*NT:  W_F^(t*(tid + v*NT)) = W_F^(t*tid) * W_P^(t*v),  P <= 16 points per thread)
+__device__ __forceinline__ constexpr double root16_re(int n) {
+    constexpr double c[16] = {1.0, 0.92387953251128675613, 0.70710678118654752440, 0.38268343236508977173, 0.0, -0.38268343236508977173,
+                              -0.70710678118654752440, -0.92387953251128675613, -1.0, -0.92387953251128675613, -0.70710678118654752440,
+                              -0.38268343236508977173, 0.0, 0.38268343236508977173, 0.70710678118654752440, 0.92387953251128675613};
+    return c[n & 15];
+}
+__device__ __forceinline__ constexpr double root16_im(int n) { return -root16_re((n + 12) & 15); }   // -sin(x) = -cos(x - pi/2)
+
+// twiddles of one tail stage for the V butterflies of a thread, from the table (not register resident)
+template <typename T, int LOG2F, int LOG2P, int LNS, bool TWLDG>
+__device__ __forceinline__ void fetch_stage_twiddles(cx<T>* tw, const cx<T>* __restrict__ table, int tid) {
+    constexpr int P = 1 << LOG2P, F = 1 << LOG2F, NT = F / P;
+    constexpr int L = stage_l<LOG2F, LOG2P>(LNS), R = 1 << L, V = P / R;
+    constexpr bool LAST = (LNS + L == LOG2F);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const int k = (tid + v * NT) & ((1 << LNS) - 1);
+#pragma unroll
+        for (int t = 1; t < R; ++t) {
+            if constexpr (LAST && P <= 16) {
+                // last stage: j = tid + v*NT never wraps, so butterfly v's factors are butterfly 0's rotated by the
+                // compile-time constant W_P^(t*v): one table read per t instead of V (fewer shared-memory wavefronts)
+                if (v == 0) tw[t - 1] = ld_tw<TWLDG, LOG2F, LOG2P, LNS>(table, t, k);
+                else tw[v * (R - 1) + (t - 1)] = cmul(tw[t - 1], mkcx<T>((T)root16_re(t * v * (16 / P)), (T)root16_im(t * v * (16 / P))));
+            } else {
+                tw[v * (R - 1) + (t - 1)] = ld_tw<TWLDG, LOG2F, LOG2P, LNS>(table, t, k);
+            }
+        }
+    }
+}
+
 template <typename T, int LOG2F, int LOG2P, bool TWREGS, bool DBUF, int LNS, int OFS, int XI, bool TWLDG = true, typename Sync>
 __device__ __forceinline__ void fft_tail(cx<T> (&b)[1 << LOG2P], const cx<T>* twl, const cx<T>* __restrict__ table,
                                          cx<T>* buf0, cx<T>* buf1, int tid, Sync sync) {
@@ -266,12 +299,7 @@ __device__ __forceinline__ void fft_tail(cx<T> (&b)[1 << LOG2P], const cx<T>* tw
             butterflies<T, P, R, true>(b, twl + OFS);
         } else {
             cx<T> tw[V * (R - 1)];
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-                const int k = (tid + v * NT) & ((1 << LNS) - 1);
-#pragma unroll
-                for (int t = 1; t < R; ++t) tw[v * (R - 1) + (t - 1)] = ld_tw<TWLDG, LOG2F, LOG2P, LNS>(table, t, k);
-            }
+            fetch_stage_twiddles<T, LOG2F, LOG2P, LNS, TWLDG>(tw, table, tid);
             butterflies<T, P, R, true>(b, tw);
         }
         fft_tail<T, LOG2F, LOG2P, TWREGS, DBUF, LNS + L, OFS + V * (R - 1), XI + 1, TWLDG>(b, twl, table, buf0, buf1, tid, sync);
@@ -294,12 +322,7 @@ __device__ __forceinline__ void fft_tail_first(cx<T> (&b)[1 << LOG2P], const cx<
         butterflies<T, P, R, true>(b, twl);
     } else {
         cx<T> tw[V * (R - 1)];
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-            const int k = (tid + v * NT) & ((1 << LNS) - 1);
-#pragma unroll
-            for (int t = 1; t < R; ++t) tw[v * (R - 1) + (t - 1)] = ld_tw<TWLDG, LOG2F, LOG2P, LNS>(table, t, k);
-        }
+        fetch_stage_twiddles<T, LOG2F, LOG2P, LNS, TWLDG>(tw, table, tid);
         butterflies<T, P, R, true>(b, tw);
     }
     fft_tail<T, LOG2F, LOG2P, TWREGS, DBUF, LNS + L, V * (R - 1), 1, TWLDG>(b, twl, table, buf0, buf1, tid, sync);
