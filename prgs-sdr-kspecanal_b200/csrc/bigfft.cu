@@ -55,6 +55,8 @@ struct BigFft {
     cd *dTwM = nullptr, *dTw1 = nullptr, *dTw2 = nullptr, *dChirp = nullptr, *dV = nullptr, *dZ = nullptr, *dP = nullptr;
     int64_t* dOffs = nullptr;
     int nOffs = 0;
+    cd* dPw = nullptr;          // Bluestein: product slabs, one per frame of a chunk (dP is the single slab used at plan time)
+    size_t zCap = 0;            // bytes allocated for dZ (and dPw)
 };
 
 static int ilog2(int64_t v) { int l = 0; while (((int64_t)1 << l) < v) ++l; return l; }
@@ -62,7 +64,7 @@ static int ilog2(int64_t v) { int l = 0; while (((int64_t)1 << l) < v) ++l; retu
 void bigfft_destroy(BigFft* b) {
     if (!b) return;
     for (void* p : {(void*)b->dWin, (void*)b->dTwM, (void*)b->dTw1, (void*)b->dTw2, (void*)b->dChirp, (void*)b->dV, (void*)b->dZ,
-                    (void*)b->dP, (void*)b->dOffs})
+                    (void*)b->dP, (void*)b->dOffs, (void*)b->dPw})
         if (p) cudaFree(p);
     delete b;
 }
@@ -127,6 +129,7 @@ BigFft* bigfft_create(int prec, int inFmt, int64_t F, int path, int64_t* convSiz
         BCK(cudaMalloc(&b->dTwM, (size_t)M * 16));
         twiddle_init_kernel<<<1024, 256, 0, st>>>(b->dTwM, M);
         BCK(cudaMalloc(&b->dZ, (size_t)M * 16));
+        b->zCap = 0;            // (re)sized per batch in bigfft_run; this slab serves the chirp spectrum below
     }
     if (path == KSPEC_PATH_BLUESTEIN) {
         BCK(cudaMalloc(&b->dChirp, (size_t)F * 16));
@@ -177,39 +180,61 @@ int bigfft_run(BigFft* b, const void* samples, int64_t scanStride, int64_t nScan
     const int64_t L1 = (int64_t)1 << b->l1, L2 = (int64_t)1 << b->l2;
     BigGeom g{b->M, b->F, b->l1, b->l2};
     const bool blue = b->path == KSPEC_PATH_BLUESTEIN;
-    for (int64_t s = 0; s < nScans && !e; ++s) {
-        for (int f = 0; f < nFrames && !e; ++f) {
-            const int64_t base = s * scanStride + frameOffs[f];
-            // pass 1: columns of the (zero padded) frame
-            if (b->inFmt == KSPEC_IN_U8_IQ) {
-                OpColsIn<KSPEC_IN_U8_IQ> op{g, samples, base, b->dWin, blue ? b->dChirp : nullptr, b->dTwM, b->dZ, b->u8off, b->u8scale};
-                e = big_cols_in(b->inFmt, b->l1, &op, b->dTw1, L2, b->smCount, st);
-            } else if (b->inFmt == KSPEC_IN_C64) {
-                OpColsIn<KSPEC_IN_C64> op{g, samples, base, b->dWin, blue ? b->dChirp : nullptr, b->dTwM, b->dZ, b->u8off, b->u8scale};
-                e = big_cols_in(b->inFmt, b->l1, &op, b->dTw1, L2, b->smCount, st);
-            } else {
-                OpColsIn<KSPEC_IN_C128> op{g, samples, base, b->dWin, blue ? b->dChirp : nullptr, b->dTwM, b->dZ, b->u8off, b->u8scale};
-                e = big_cols_in(b->inFmt, b->l1, &op, b->dTw1, L2, b->smCount, st);
-            }
-            *launches += 1;
-            if (e) break;
-            if (!blue) {
-                // pass 2: rows -> |X| cumulated into acc, stored [k1][k2] (the epilogue un-permutes)
-                OpRowsAcc op{g, b->dZ, dAcc + s * b->F, 1.0, cumuMode, f == 0 ? 1 : 0, 1};
-                e = big_rows_acc(b->l2, op, b->dTw2, L1, b->smCount, st);
-                *launches += 1;
-            } else {
-                OpRowsMul om{g, b->dZ, b->dV, b->dP};
-                e = big_rows_mul(b->l2, om, b->dTw2, L1, b->smCount, st);
-                if (e) break;
-                OpColsMid oc{g, b->dP, b->dTwM, b->dZ};
-                e = big_cols_mid(b->l1, oc, b->dTw1, L2, b->smCount, st);
-                if (e) break;
-                OpRowsAcc oa{g, b->dZ, dAcc + s * b->F, 1.0 / (double)b->M, cumuMode, f == 0 ? 1 : 0, 0};
-                e = big_rows_acc(b->l2, oa, b->dTw2, L1, b->smCount, st);
-                *launches += 3;
-            }
+    if (b->nOffs != nFrames) {
+        if (b->dOffs) cudaFree(b->dOffs);
+        b->dOffs = nullptr;
+        if (cudaMalloc(&b->dOffs, (size_t)nFrames * 8) != cudaSuccess) { set_error("frame table allocation failed"); return KSPEC_ERR_NOMEM; }
+        b->nOffs = nFrames;
+    }
+    cudaMemcpyAsync(b->dOffs, frameOffs, (size_t)nFrames * 8, cudaMemcpyHostToDevice, st);
+    // scans are processed in chunks whose work vectors (one M-point slab per frame) stay within ~1 GiB each
+    const size_t slab = (size_t)b->M * 16;
+    int64_t chunk = (int64_t)(((size_t)1 << 30) / (slab * (size_t)nFrames));
+    if (chunk < 1) chunk = 1;
+    if (chunk > nScans) chunk = nScans;
+    const size_t need = slab * (size_t)nFrames * (size_t)chunk;
+    if (b->zCap < need) {
+        if (b->dZ) cudaFree(b->dZ);
+        if (b->dPw) cudaFree(b->dPw);
+        b->dZ = b->dPw = nullptr; b->zCap = 0;
+        if (cudaMalloc(&b->dZ, need) != cudaSuccess || (blue && cudaMalloc(&b->dPw, need) != cudaSuccess)) {
+            cudaGetLastError();
+            set_error("multi-pass work buffers (%zu bytes) do not fit in device memory", need);
+            return KSPEC_ERR_NOMEM;
         }
+        b->zCap = need;
+    }
+    const size_t eb = b->inFmt == KSPEC_IN_U8_IQ ? 2 : (b->inFmt == KSPEC_IN_C64 ? 8 : 16);
+    for (int64_t s0 = 0; s0 < nScans && !e; s0 += chunk) {
+        const int64_t ns = (nScans - s0 < chunk) ? nScans - s0 : chunk;
+        const int64_t nfs = ns * nFrames;
+        const void* smp = reinterpret_cast<const unsigned char*>(samples) + (size_t)s0 * scanStride * eb;
+        // pass 1: columns of every (zero padded) frame of the chunk
+        if (b->inFmt == KSPEC_IN_U8_IQ) {
+            OpColsIn<KSPEC_IN_U8_IQ> op{g, smp, scanStride, b->dOffs, nFrames, b->dWin, blue ? b->dChirp : nullptr, b->dTwM, b->dZ, b->u8off, b->u8scale};
+            e = big_cols_in(b->inFmt, b->l1, &op, b->dTw1, nfs * L2, b->smCount, st);
+        } else if (b->inFmt == KSPEC_IN_C64) {
+            OpColsIn<KSPEC_IN_C64> op{g, smp, scanStride, b->dOffs, nFrames, b->dWin, blue ? b->dChirp : nullptr, b->dTwM, b->dZ, b->u8off, b->u8scale};
+            e = big_cols_in(b->inFmt, b->l1, &op, b->dTw1, nfs * L2, b->smCount, st);
+        } else {
+            OpColsIn<KSPEC_IN_C128> op{g, smp, scanStride, b->dOffs, nFrames, b->dWin, blue ? b->dChirp : nullptr, b->dTwM, b->dZ, b->u8off, b->u8scale};
+            e = big_cols_in(b->inFmt, b->l1, &op, b->dTw1, nfs * L2, b->smCount, st);
+        }
+        *launches += 1;
+        if (e) break;
+        if (blue) {
+            OpRowsMul om{g, b->dZ, b->dV, b->dPw};
+            e = big_rows_mul(b->l2, om, b->dTw2, nfs * L1, b->smCount, st);
+            if (e) break;
+            OpColsMid oc{g, b->dPw, b->dTwM, b->dZ};
+            e = big_cols_mid(b->l1, oc, b->dTw1, nfs * L2, b->smCount, st);
+            if (e) break;
+            *launches += 2;
+        }
+        // last pass: rows, |X|, cumulate over the frames of each scan in registers
+        RowsAccParams ra{g, b->dZ, dAcc + s0 * b->F, blue ? 1.0 / (double)b->M : 1.0, cumuMode, nFrames, blue ? 0 : 1};
+        e = big_rows_acc(b->l2, ra, b->dTw2, ns * L1, b->smCount, st);
+        *launches += 1;
     }
     if (e) { set_error("multi-pass FFT launch failed: %s", cudaGetErrorString((cudaError_t)e)); return KSPEC_ERR_CUDA; }
     return KSPEC_OK;

@@ -27,27 +27,33 @@ struct BigGeom {
 
 // ---- pass ops ---------------------------------------------------------------------------------------------------
 // Every op provides   cd load(int64_t q, int e)   and   void store(int64_t q, int k, cd v)   for batch item q.
+// One launch covers every frame of every scan of a chunk: q = fs * L2 + n2 (column passes) or fs * L1 + k1 (row passes),
+// fs = scan * nFrames + frame; the work vectors Z and P hold one M-point slab per fs.
 
 // column pass, first transform: gather the frame (fused ingest, window, optional chirp, zero padding)
 template <int INFMT> struct OpColsIn {
     BigGeom g;
-    const void* samples; int64_t frameBase;
+    const void* samples; int64_t scanStride; const int64_t* offs; int nFrames;
     const double* win; const cd* chirp;   // chirp == nullptr for the plain four-step transform
     const cd* twM; cd* Z;
     double u8off, u8scale;
     __device__ __forceinline__ cd load(int64_t q, int e) const {
-        const int64_t n = ((int64_t)e << g.l2) + q;
+        const int64_t fs = q >> g.l2, n2 = q & (((int64_t)1 << g.l2) - 1);
+        const int64_t n = ((int64_t)e << g.l2) + n2;
         if (n >= g.F) return make_double2(0.0, 0.0);
-        cd v = Ingest<double, INFMT>::load(samples, frameBase + n, __ldg(&win[n]), u8off, u8scale);
+        const int64_t s = fs / nFrames;
+        const int64_t base = s * scanStride + __ldg(&offs[fs - s * nFrames]);
+        cd v = Ingest<double, INFMT>::load(samples, base + n, __ldg(&win[n]), u8off, u8scale);
         if (chirp) v = cmul(v, __ldg(&chirp[n]));
         return v;
     }
     __device__ __forceinline__ void store(int64_t q, int k, cd v) const {
-        Z[((int64_t)k << g.l2) + q] = cmul(v, __ldg(&twM[q * k]));
+        const int64_t fs = q >> g.l2, n2 = q & (((int64_t)1 << g.l2) - 1);
+        Z[fs * g.M + ((int64_t)k << g.l2) + n2] = cmul(v, __ldg(&twM[n2 * k]));
     }
 };
 
-// column pass on a natural-order device vector (precomputing V)
+// column pass on a natural-order device vector (precomputing V; single slab)
 struct OpColsPlain {
     BigGeom g; const cd* X; const cd* twM; cd* Z;
     __device__ __forceinline__ cd load(int64_t q, int e) const { return X[((int64_t)e << g.l2) + q]; }
@@ -58,15 +64,19 @@ struct OpColsPlain {
 struct OpColsMid {
     BigGeom g; const cd* P; const cd* twM; cd* Z;
     __device__ __forceinline__ cd load(int64_t q, int e) const {
-        // element n = e*L2 + q of the natural-order vector lives at (n mod L1)*L2 + n div L1   (L2 >= L1)
+        // element n = e*L2 + n2 of the natural-order vector lives at (n mod L1)*L2 + n div L1   (L2 >= L1)
+        const int64_t fs = q >> g.l2, n2 = q & (((int64_t)1 << g.l2) - 1);
         const int64_t L1m = ((int64_t)1 << g.l1) - 1;
-        const int64_t loc = ((q & L1m) << g.l2) + ((int64_t)e << (g.l2 - g.l1)) + (q >> g.l1);
-        return P[loc];
+        const int64_t loc = ((n2 & L1m) << g.l2) + ((int64_t)e << (g.l2 - g.l1)) + (n2 >> g.l1);
+        return P[fs * g.M + loc];
     }
-    __device__ __forceinline__ void store(int64_t q, int k, cd v) const { Z[((int64_t)k << g.l2) + q] = cmul(v, __ldg(&twM[q * k])); }
+    __device__ __forceinline__ void store(int64_t q, int k, cd v) const {
+        const int64_t fs = q >> g.l2, n2 = q & (((int64_t)1 << g.l2) - 1);
+        Z[fs * g.M + ((int64_t)k << g.l2) + n2] = cmul(v, __ldg(&twM[n2 * k]));
+    }
 };
 
-// row pass storing the spectrum as is, layout [k1*L2 + k2] (precomputing V)
+// row pass storing the spectrum as is, layout [k1*L2 + k2] (precomputing V; single slab)
 struct OpRowsPlain {
     BigGeom g; const cd* Z; cd* out;
     __device__ __forceinline__ cd load(int64_t q, int e) const { return Z[(q << g.l2) + e]; }
@@ -76,28 +86,14 @@ struct OpRowsPlain {
 // row pass of the first Bluestein transform: P = conj(U . V)
 struct OpRowsMul {
     BigGeom g; const cd* Z; const cd* V; cd* P;
-    __device__ __forceinline__ cd load(int64_t q, int e) const { return Z[(q << g.l2) + e]; }
-    __device__ __forceinline__ void store(int64_t q, int k, cd v) const {
-        const int64_t i = (q << g.l2) + k;
-        P[i] = cconj(cmul(v, __ldg(&V[i])));
+    __device__ __forceinline__ cd load(int64_t q, int e) const {
+        const int64_t fs = q >> g.l1, k1 = q & (((int64_t)1 << g.l1) - 1);
+        return Z[fs * g.M + (k1 << g.l2) + e];
     }
-};
-
-// final row pass: |X| (scaled), cumulate over frames (data_cumu, K:124-147) into acc
-struct OpRowsAcc {
-    BigGeom g; const cd* Z; double* acc; double scale; int cumuMode; int first; int transposedAcc;
-    __device__ __forceinline__ cd load(int64_t q, int e) const { return Z[(q << g.l2) + e]; }
     __device__ __forceinline__ void store(int64_t q, int k, cd v) const {
-        const int64_t bin = q + ((int64_t)k << g.l1);
-        if (bin >= g.F) return;
-        const int64_t i = transposedAcc ? (q << g.l2) + k : bin;
-        const double mag = sqrt(v.x * v.x + v.y * v.y) * scale;
-        double a = mag;
-        if (!first) {
-            const double o = acc[i];
-            a = cumuMode == KSPEC_CUMU_AVG ? (o + mag) / 2 : cumuMode == KSPEC_CUMU_MAX ? fmax(o, mag) : cumuMode == KSPEC_CUMU_MIN ? fmin(o, mag) : mag;
-        }
-        acc[i] = a;
+        const int64_t fs = q >> g.l1, k1 = q & (((int64_t)1 << g.l1) - 1);
+        const int64_t i = (k1 << g.l2) + k;
+        P[fs * g.M + i] = cconj(cmul(v, __ldg(&V[i])));
     }
 };
 
@@ -150,6 +146,74 @@ static int launch_team_fft(const Op& op, const cd* tw, int64_t nBatch, int smCou
     int64_t cap = (int64_t)smCount * 4;
     int grid = (int)(need < cap ? need : cap);
     k<<<grid, C::CTA, C::SMEM_BYTES, st>>>(op, tw, nBatch);
+    return (int)cudaGetLastError();
+}
+
+// final row pass: a team owns row k1 of one scan and walks the scan's frames, |X| (scaled) cumulated in the registers
+// that own the bins (data_cumu, K:124-147); one store per bin and scan.  acc layout: [k1][k2] (four-step; the epilogue
+// un-permutes) or natural bin order (Bluestein, only bins < F exist).
+struct RowsAccParams {
+    BigGeom g; const cd* Z; double* acc; double scale; int cumuMode; int nFrames; int transposedAcc;
+};
+
+template <int LOG2L>
+__global__ void __launch_bounds__(SmemCfg<double, LOG2L>::CTA, 1)
+team_fft_acc_kernel(const RowsAccParams p, const cd* __restrict__ tw, int64_t nBatch) {
+    using C = SmemCfg<double, LOG2L>;
+    constexpr int P = C::P, NT = C::NT, TEAMS = C::TEAMS, LOG2P = C::LOG2P;
+    constexpr int L0 = stage_l<LOG2L, LOG2P>(0);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int team = (TEAMS > 1) ? (threadIdx.x / NT) : 0;
+    const int tid = (TEAMS > 1) ? (threadIdx.x % NT) : threadIdx.x;
+    cd* bufA = reinterpret_cast<cd*>(smem_raw) + team * C::FPAD;
+    cd* bufB = C::DBUF ? bufA + TEAMS * C::FPAD : bufA;
+    auto sync = [] { __syncthreads(); };
+    const int64_t perIter = (int64_t)gridDim.x * TEAMS;
+    const int64_t iters = (nBatch + perIter - 1) / perIter;
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t q = it * perIter + (int64_t)blockIdx.x * TEAMS + team;
+        const bool valid = q < nBatch;
+        const int64_t qc = valid ? q : nBatch - 1;
+        const int64_t s = qc >> p.g.l1, k1 = qc & (((int64_t)1 << p.g.l1) - 1);
+        double a[P];
+        for (int f = 0; f < p.nFrames; ++f) {
+            const cd* row = p.Z + (s * p.nFrames + f) * p.g.M + (k1 << p.g.l2);
+            cd b[P];
+#pragma unroll
+            for (int m = 0; m < P; ++m) b[m] = row[tid + NT * m];
+            butterflies<double, P, (1 << L0), false>(b, nullptr);
+            fft_tail<double, LOG2L, LOG2P, false, C::DBUF, L0, 0, 0>(b, nullptr, tw, bufA, bufB, tid, sync);
+            if constexpr (C::DBUF && (C::NX & 1)) { cd* t = bufA; bufA = bufB; bufB = t; }
+#pragma unroll
+            for (int m = 0; m < P; ++m) {
+                const double mag = sqrt(b[m].x * b[m].x + b[m].y * b[m].y) * p.scale;
+                if (f == 0 || p.cumuMode == KSPEC_CUMU_RAW) a[m] = mag;
+                else if (p.cumuMode == KSPEC_CUMU_AVG) a[m] = (a[m] + mag) / 2;
+                else if (p.cumuMode == KSPEC_CUMU_MAX) a[m] = fmax(a[m], mag);
+                else a[m] = fmin(a[m], mag);
+            }
+        }
+        if (valid) {
+#pragma unroll
+            for (int m = 0; m < P; ++m) {
+                const int k = tid + NT * m;
+                const int64_t bin = k1 + ((int64_t)k << p.g.l1);
+                if (bin < p.g.F) p.acc[s * p.g.F + (p.transposedAcc ? (k1 << p.g.l2) + k : bin)] = a[m];
+            }
+        }
+    }
+}
+
+template <int LOG2L>
+static int launch_team_fft_acc(const RowsAccParams& p, const cd* tw, int64_t nBatch, int smCount, cudaStream_t st) {
+    using C = SmemCfg<double, LOG2L>;
+    auto k = team_fft_acc_kernel<LOG2L>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    int64_t need = (nBatch + C::TEAMS - 1) / C::TEAMS;
+    int64_t cap = (int64_t)smCount * 4;
+    int grid = (int)(need < cap ? need : cap);
+    k<<<grid, C::CTA, C::SMEM_BYTES, st>>>(p, tw, nBatch);
     return (int)cudaGetLastError();
 }
 
@@ -251,7 +315,7 @@ int big_cols_plain(int l1, const OpColsPlain& op, const cd* tw, int64_t nBatch, 
 int big_cols_mid(int l1, const OpColsMid& op, const cd* tw, int64_t nBatch, int smCount, cudaStream_t st);
 int big_rows_plain(int l2, const OpRowsPlain& op, const cd* tw, int64_t nBatch, int smCount, cudaStream_t st);
 int big_rows_mul(int l2, const OpRowsMul& op, const cd* tw, int64_t nBatch, int smCount, cudaStream_t st);
-int big_rows_acc(int l2, const OpRowsAcc& op, const cd* tw, int64_t nBatch, int smCount, cudaStream_t st);
+int big_rows_acc(int l2, const RowsAccParams& p, const cd* tw, int64_t nBatch, int smCount, cudaStream_t st);
 int big_plain(int l, const OpPlain& op, const cd* tw, int64_t nBatch, int smCount, cudaStream_t st);
 int big_blue_small(int inFmt, int logM, const BlueSmallParams& p, int smCount, cudaStream_t st);
 
