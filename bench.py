@@ -226,14 +226,18 @@ def run_ours(args):
     for i in range(N_SCANS // BASE_SCANS):
         plan.dev_upload(d_samples, base, offset=i * base.nbytes)
     # pinned host copy for the end-to-end leg
-    pinned = _ffi.PinnedBuffer(N_SCANS * S * 8)
-    host = pinned.view(np.complex64)
-    for i in range(N_SCANS // BASE_SCANS):
-        host[i * len(base):(i + 1) * len(base)] = base
+    host = None
+    if not os.environ.get("KSPEC_BENCH_FAST"):
+        pinned = _ffi.PinnedBuffer(N_SCANS * S * 8)
+        host = pinned.view(np.complex64)
+        for i in range(N_SCANS // BASE_SCANS):
+            host[i * len(base):(i + 1) * len(base)] = base
 
     comm = None
     if world > 1:
         comm = _make_comm(world, rank, local, dist)
+        plan.reserve_sms(int(os.environ.get("KSPEC_SM_RESERVE", "0")))      # measured: reserving SMs for the NCCL kernels does not pay (profiles/README.md)
+    comm_sync = bool(int(os.environ.get("KSPEC_COMM_SYNC", "0")))
     total_scans = N_SCANS * world
     base_idx = rank * N_SCANS
 
@@ -246,7 +250,9 @@ def run_ours(args):
         plan.zerospan_batch_dev(d_samples, N_SCANS, GAIN, XRES, "MAX", rows=None, want_hm=True,
                                 scan_index_base=base_idx, n_scans_total=total_scans)
         if comm is not None:
-            comm.allreduce_plan_stats(plan)
+            comm.allreduce_plan_stats(plan)          # asynchronous: overlaps the next step's kernel
+            if comm_sync:
+                comm.join(plan)
 
     def step_e2e():
         out = plan.zerospan_batch(host, N_SCANS, GAIN, XRES, "MAX", rows=None, want_hm=True,

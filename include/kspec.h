@@ -160,6 +160,9 @@ int kspec_timer_stop(kspec_plan* plan, float* ms);
 /* durations (ms, CUDA events on the plan's stream) of the most recent fused scan-kernel launches, oldest first;
  * at most 64 are kept.  Synchronises the stream. */
 int kspec_kernel_times(kspec_plan* plan, float* ms, int cap, int* n);
+/* leave nSMs streaming multiprocessors out of the fused kernel's grid so that kernels of other streams -- the NCCL exchange
+ * of the previous batch -- can run beside it (default 0) */
+int kspec_plan_reserve_sms(kspec_plan* plan, int nSMs);
 /* number of kernels this plan has launched since creation (bench "gpu_launches") */
 int kspec_launch_count(const kspec_plan* plan, int64_t* n);
 

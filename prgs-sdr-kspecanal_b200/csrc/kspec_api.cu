@@ -64,6 +64,7 @@ struct kspec_plan {
     cudaStream_t st = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int smCount = 0;
+    int smReserve = 0;
     SmemKernelInfo ki{};          // base variant of the fused kernel
     SmemKernelInfo kiMulti{};     // multi-team variant (ctasPerSm == 0: not available for this shape)
     int64_t convSize = 0;
@@ -136,7 +137,9 @@ int run_engine(kspec_plan* pl, ScanParams& p, int* slotsOut) {
         const int variant = multi ? SMEM_VARIANT_MULTI : SMEM_VARIANT_BASE;
         const int teams = ki.teams;
         int64_t need = (p.nScans + teams - 1) / teams;
-        int64_t cap = (int64_t)pl->smCount * (ki.ctasPerSm > 0 ? ki.ctasPerSm : 1);
+        // smReserve SMs are left to concurrent kernels (the NCCL exchange of the previous batch, kspec_comm_allreduce_plan)
+        const int sms = pl->smCount - pl->smReserve > 0 ? pl->smCount - pl->smReserve : 1;
+        int64_t cap = (int64_t)sms * (ki.ctasPerSm > 0 ? ki.ctasPerSm : 1);
         int grid = (int)(need < cap ? need : cap);
         if (grid < 1) grid = 1;
         const int slots = grid * teams;
@@ -759,6 +762,11 @@ int kspec_kernel_times(kspec_plan* pl, float* ms, int cap, int* n) {
         CK(cudaEventElapsedTime(&ms[i], pl->kev[ks][0], pl->kev[ks][1]));
     }
     *n = (int)have;
+    return KSPEC_OK;
+}
+int kspec_plan_reserve_sms(kspec_plan* pl, int nSMs) {
+    if (check_plan(pl) || nSMs < 0 || nSMs >= pl->smCount) { set_error("bad SM reserve"); return KSPEC_ERR_ARG; }
+    pl->smReserve = nSMs;
     return KSPEC_OK;
 }
 int kspec_launch_count(const kspec_plan* pl, int64_t* n) {

@@ -73,6 +73,7 @@ SIGNATURES = {
     "kspec_timer_start": (C.c_int, [_P]),
     "kspec_timer_stop": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "kspec_kernel_times": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]),
+    "kspec_plan_reserve_sms": (C.c_int, [_P, C.c_int]),
     "kspec_launch_count": (C.c_int, [_P, C.POINTER(_I64)]),
     "kspec_comm_unique_id": (C.c_int, [C.c_char_p]),
     "kspec_comm_init": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_char_p, C.c_int]),

@@ -230,6 +230,10 @@ class Plan:
         check(_ffi.lib().kspec_kernel_times(self._h, ms, cap, C.byref(n)))
         return [ms[i] for i in range(n.value)]
 
+    def reserve_sms(self, n):
+        """leave n SMs to concurrent kernels (the asynchronous NCCL exchange)"""
+        check(_ffi.lib().kspec_plan_reserve_sms(self._h, int(n)))
+
     def launch_count(self):
         n = C.c_int64(0)
         check(_ffi.lib().kspec_launch_count(self._h, C.byref(n)))
