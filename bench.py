@@ -120,6 +120,33 @@ def profiled_traffic():
     return (tot or None), os.path.relpath(files[-1], ROOT)
 
 
+def bind_to_gpu_numa_node(local):
+    """pin this rank (and therefore its pinned host buffers, first touch) to the NUMA node of its GPU: with 8 ranks the
+    end-to-end leg is bound by host memory / PCIe root complexes, not by the GPUs"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = int(vis.split(",")[local]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else local
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bdf = bus.lower()[-12:]                     # 0000:1b:00.0
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def base_capture():
     from kspec import synth
     return synth.tones_noise(BASE_SCANS * S, seed=1)
@@ -212,6 +239,7 @@ def run_ours(args):
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     from kspec import _ffi
     from kspec.engine import Plan
     from oracle import kspec_oracle as O          # cpu_baseline leg + window table only
@@ -306,6 +334,10 @@ def run_ours(args):
         k_ms = float(np.mean(kt)) if kt else ms / args.steps
         ach = algorithmic_bytes(N_SCANS) / (k_ms * 1e-3) / 1e9
         # cpu baseline: bounded sample, all host cores
+        try:
+            os.sched_setaffinity(0, range(os.cpu_count() or 1))      # the CPU baseline may use every core again
+        except Exception:
+            pass
         cores = min(os.cpu_count() or 1, 64)
         cpu_v = cpu_reference(cores, 640, reps=2)
         cpu_1 = cpu_reference(1, 640)
@@ -314,7 +346,7 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_all / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": plan.precision, "data": "synthetic",
             "config": {"workload": WORKLOAD, "l2": "input %.2f GiB per step >> 126 MB L2, no flush needed" % (N_SCANS * S * 8 / 2 ** 30),
-                       "frames_per_s": value * 1e6 * info.n_frames / S, "parallelism": "scan-range shards x%d" % world,
+                       "frames_per_s": value * 1e6 * info.n_frames / S, "parallelism": "scan-range shards x%d" % world, "numa_node_rank0": numa,
                        "cta_threads": info.cta_threads, "ctas_per_sm": info.ctas_per_sm, "smem_bytes": info.smem_bytes},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": profiled_traffic()[0], "traffic_source": profiled_traffic()[1],

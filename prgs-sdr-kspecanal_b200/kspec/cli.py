@@ -95,10 +95,17 @@ def do_run(d):
     if d["prgMode"] == "SCAN":
         freqs, _ = H.scan_range(d)
         return dict(freqs=freqs)
-    if d["prgMode"] == "ZEROSPANSAVE":
-        return dict(nScans=H.zero_span_save(d))
     if d["prgMode"] == "ZEROSPANPLAY":
         return dict(nScans=H.zero_span_play_all(d))
+    if d.get("iqFile"):                                        # raw uint8 capture: bytes go to the GPU unconverted
+        if d["prgMode"] == "ZEROSPANSAVE":
+            with open(d["zeroSpanSaveFile"], "wb+") as f:
+                for k in ("centerFreq", "samplingRate", "gain"):   # K:512-514
+                    H.pickle.dump(d[k], f)
+                return dict(nScans=H.zero_span_u8_file(d, d["iqFile"], save=f))
+        return dict(nScans=H.zero_span_u8_file(d, d["iqFile"]))
+    if d["prgMode"] == "ZEROSPANSAVE":
+        return dict(nScans=H.zero_span_save(d))
     return dict(nScans=H.zero_span(d))
 
 
@@ -108,7 +115,7 @@ def main(argv=None):
     handle_args(d, argv)
     if not d.get("iqFile"):                                    # synthetic source: bounded run unless told otherwise
         d["prgLoopCnt"] = min(d["prgLoopCnt"], 2 if d["prgMode"] == "SCAN" else 256)
-    if d["prgMode"] != "ZEROSPANPLAY":
+    if d["prgMode"] == "SCAN" or (d["prgMode"] != "ZEROSPANPLAY" and not d.get("iqFile")):
         d["sdr"] = make_source(d)
     print("INFO: prgMode[{}] fftSize[{}] fullSize[{}] window[{}] curScanNonOverlap[{}] xRes[{}]".format(
         d["prgMode"], d["fftSize"], d["fullSize"], d["window"], d["curScanNonOverlap"], d["xRes"]))

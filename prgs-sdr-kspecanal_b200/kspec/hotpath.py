@@ -213,6 +213,41 @@ def zero_span(d, block=64):
     return done
 
 
+def zero_span_u8_file(d, path, block=256, save=None, clock=time.time):
+    """zeroSpan / zeroSpanSave over an rtl_sdr raw capture (interleaved uint8 I,Q, octave/load_rtlsdr.m:8-12) without the
+    detour through complex128: the bytes are memory-mapped and handed to the GPU as they are (2 B per sample over PCIe, the
+    uint8 -> float conversion is fused into the first FFT stage).  Scan k = samples [k*fullSize, (k+1)*fullSize), at most
+    prgLoopCnt scans.  ``save``: optional open file; the zeroSpanSave records (K:523-525) are appended to it."""
+    raw = np.memmap(path, dtype=np.uint8, mode="r")
+    S = int(d["fullSize"])
+    n_total = min(int(d["prgLoopCnt"]), len(raw) // (2 * S))
+    zero_span_init(d)
+    plan = _plan(d, _ffi.IN_U8_IQ)
+    done = 0
+    while done < n_total and not d["cmd.stop"]:
+        n = min(block, n_total - done)
+        chunk = np.ascontiguousarray(raw[2 * S * done:2 * S * (done + n)])
+        state = None
+        if d.get("Fft.Max") is not None:
+            state = (d["Fft.Max"], d["Fft.Min"], d["Fft.Avg"])
+        adj = d["Fft.Adj"] if d.get("AdjSigLvls", "") != "" else None
+        t = clock()
+        out = plan.zerospan_batch(chunk, n, d["gain"], d["xRes"], d["pltCompressHM"], adj=adj,
+                                  rows="linear" if save is not None else "db", want_hm=True, state=state)
+        d["Fft.Max"], d["Fft.Min"], d["Fft.Avg"] = out["max"], out["min"], out["avg"]
+        if save is not None:
+            for row in out["rows"]:
+                pickle.dump(t, save)
+                pickle.dump(np.array(row), save)
+        else:
+            d["Fft.Cur"] = out["rows"][-1]
+        for r in out["hm_rows"]:
+            d["fftHM"][d["fftHMIndex"], :] = r
+            d["fftHMIndex"] = (d["fftHMIndex"] + 1) % HEATMAP_ROWS
+        done += n
+    return done
+
+
 # ------------------------------------------------------------------------------------------------------
 # zeroSpanSave / zeroSpanPlay streams (K:509-564): format unchanged, FFT work batched on the GPU
 # ------------------------------------------------------------------------------------------------------
