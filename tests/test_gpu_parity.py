@@ -172,6 +172,71 @@ def test_big_engines(F, r, wname, mode, fmt):
         assert np.max(np.abs(z[k] - refz[kk])) < F64_TOL, k
 
 
+def test_cfg2_full_size_quickfullscan():
+    """BASELINE cfg 2 at full size: quickFullScan 30 MHz..1.5 GHz -> 613 groups, 39 232 entries, fftSize 64, ones, r = 0.1
+    (71 frames per step); 613 steps at scanRangeNonOverlap 1.0 and 1226 at the alias' default 0.5; two passes; vs the oracle."""
+    F, r = 64, 0.1
+    S = O.full_size(F, FS)
+    win = np.ones(F)
+    start, end, _ = O.fixup_scan_range(30e6, 1.5e9, FS)
+    assert end == 1.5012e9
+    for R, n_steps in ((1.0, 613), (0.5, 1226)):
+        geo = O.scan_geometry(start, end, FS, F, R)
+        num_groups, total, steps = geo
+        assert (num_groups, total, len(steps)) == (613, 39232, n_steps)
+        bufs = np.concatenate([synth.step_tones(s, S) for s in range(n_steps)])
+        lin = [O.curscan(bufs[s * S:(s + 1) * S].astype(np.complex128), F, r, win) for s in range(n_steps)]
+        ref = O.scan_init_state(total, 19.1)
+        st = O.scan_init_state(total, 19.1)
+        ok = np.ones(n_steps, dtype=np.uint8)
+        ok[[5, 600]] = 0
+        with Plan(F, S, r, win, "AVG", precision="f32") as plan:
+            for ps in range(2):
+                O.scan_pass(lin, ok.astype(bool), geo, 19.1, ref, ps)
+                plan.scan_batch(bufs, n_steps, [s["i_start"] for s in steps], [s["i_done"] for s in steps], total,
+                                O.MIN_AMP4CLIP, 19.1, st, ps, step_ok=ok)
+                for k in ("cur", "max", "min", "avg"):
+                    assert np.max(np.abs(st[k] - ref[k])) < DB_TOL, (R, ps, k)
+        assert np.array_equal(np.argmax(st["cur"].reshape(-1, F), axis=1), np.argmax(ref["cur"].reshape(-1, F), axis=1))
+
+
+def test_cfg3_full_size_sixty_second_capture():
+    """BASELINE cfg 3 at full size: 60 s at 2.4 MS/s = 144 M samples -> 2197 scans x 29 frames, fftSize 8192, kaiser(64),
+    75 % overlap.  Size-independent properties: identical results for 1 and 4 scan-range shards (the multi-GPU contract),
+    sampled scans against the oracle, Max >= Avg >= Min."""
+    F, r, gain, xres = 8192, 0.25, 19.1, 512
+    S = O.full_size(F, FS)
+    n = int(60 * FS) // S
+    assert (S, n) == (65536, 2197)
+    win = O.window_table("kaiser", F)
+    block = synth.tones_noise(64 * S, seed=3)                       # 64-scan block, re-used with a slow gain pattern
+    gains = (0.25 + 0.75 * ((np.arange(n) // 64) % 4) / 3.0).astype(np.float32)
+    x = np.empty(n * S, dtype=np.complex64)
+    for k in range(0, n, 64):
+        m = min(64, n - k)
+        x[k * S:(k + m) * S] = block[:m * S] * gains[k]
+    with Plan(F, S, r, win, "AVG") as plan:
+        assert plan.precision == "f64" and plan.n_frames == 29
+        full = plan.zerospan_batch(x, n, gain, xres, "MAX", rows="db")
+        bounds = np.linspace(0, n, 5).astype(int)
+        parts = [plan.zerospan_batch(x[a * S:b * S], b - a, gain, xres, "MAX", scan_index_base=a, n_scans_total=n)
+                 for a, b in zip(bounds[:-1], bounds[1:])]
+    assert np.array_equal(np.max([p["max"] for p in parts], axis=0), full["max"])
+    assert np.array_equal(np.min([p["min"] for p in parts], axis=0), full["min"])
+    assert np.max(np.abs(np.sum([p["avg"] for p in parts], axis=0) - full["avg"])) < 1e-9
+    assert np.array_equal(np.vstack([p["hm_rows"] for p in parts]), full["hm_rows"])
+    assert np.all(full["max"] >= full["avg"] - 1e-12) and np.all(full["avg"] >= full["min"] - 1e-12)
+    for s in (0, 1000, 2196):
+        ref = O.log_nogain(O.curscan(x[s * S:(s + 1) * S].astype(np.complex128), F, r, win), gain)
+        assert np.max(np.abs(full["rows"][s] - ref)) < F64_TOL
+        assert int(np.argmax(full["rows"][s])) == int(np.argmax(ref))
+    # Avg after 2197 scans == the halving recurrence over the last rows (older rows weigh < 2^-64)
+    a = full["rows"][n - 80]
+    for row in full["rows"][n - 79:]:
+        a = (a + row) / 2
+    assert np.max(np.abs(a - full["avg"])) < 1e-9
+
+
 def test_cfg4_full_size_two_to_the_21():
     """BASELINE cfg 4: fftSize 2^21, ones window, cumulate MAX, curScanNonOverlap 0.1 -> 11 frames per 2^22-sample scan"""
     F, r = 1 << 21, 0.1
