@@ -239,7 +239,7 @@ def run_ours(args):
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    numa = bind_to_gpu_numa_node(local) if world > 1 else None
+    numa = bind_to_gpu_numa_node(local) if not os.environ.get("KSPEC_NO_NUMA_BIND") else None
     from kspec import _ffi
     from kspec.engine import Plan
     from oracle import kspec_oracle as O          # cpu_baseline leg + window table only

@@ -21,11 +21,12 @@ namespace kspec {
 // VAR selects a tuning variant of the same kernel (A/B experiments, see profiles/README.md):
 //   0 production   1 twiddles via L1 instead of registers, 4 CTAs/SM   2 as 1 without TMA staging   3 as 0 with one stage
 //   5 as 0 with 2 CTAs/SM (255 registers)   6 as 3 with the twiddles in a linearised shared-memory table
+//   7 as 4 without TMA staging (frames loaded straight from L1/L2 into registers)
 //   4 one 512-thread CTA per SM = four independent 128-thread teams (named barriers) sharing one shared-memory twiddle table
 template <typename T, int LOG2F, int VAR = 0> struct SmemCfg {
     static constexpr int LOG2P = LOG2F >= 7 ? 4 : (LOG2F >= 5 ? 3 : 2);
     static constexpr int P = 1 << LOG2P, F = 1 << LOG2F, NT = F / P;
-    static constexpr bool MULTI = (VAR == 4) && NT >= 32;  // teams of whole warps that never wait for each other
+    static constexpr bool MULTI = (VAR == 4 || VAR == 7) && NT >= 32;  // teams of whole warps that never wait for each other
     static constexpr int CTA = MULTI ? 4 * NT : (NT < 128 ? 128 : NT);
     static constexpr int TEAMS = CTA / NT;
     static constexpr bool F32 = sizeof(T) == 4;
@@ -85,7 +86,7 @@ template <typename T, int INFMT, int LOG2F, int VAR = 0> struct StageCfg {
     static constexpr bool OK = (C::TEAMS == 1 || C::MULTI) && C::DBUF;
     static constexpr int STG_AUTO = !OK ? 0 : (C::MINB * (C::SMEM_BYTES + 2 * STAGE_BYTES + 1024) <= BUDGET ? 2
                                             : (C::MINB * (C::SMEM_BYTES + STAGE_BYTES + 1024) <= BUDGET ? 1 : 0));
-    static constexpr int STG = VAR == 2 ? 0 : (C::MULTI ? 1 : ((VAR == 3 || VAR == 6) ? (STG_AUTO > 1 ? 1 : STG_AUTO) : STG_AUTO));
+    static constexpr int STG = (VAR == 2 || VAR == 7) ? 0 : (C::MULTI ? 1 : ((VAR == 3 || VAR == 6) ? (STG_AUTO > 1 ? 1 : STG_AUTO) : STG_AUTO));
     static constexpr int EX_BYTES = (C::SMEM_BYTES + 127) / 128 * 128;
     static constexpr int STAGE_TEAMS = C::MULTI ? C::TEAMS : 1;
     static constexpr int TW_OFS = EX_BYTES + STAGE_TEAMS * STG * STAGE_BYTES;

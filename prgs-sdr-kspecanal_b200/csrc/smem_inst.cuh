@@ -19,6 +19,7 @@ int KSPEC_INST_NAME(int log2F, int variant, const ScanParams& p, int grid, cudaS
             if (var == 1) return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, 11, 1>(p, grid, st, info);
             if (var == 2) return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, 11, 2>(p, grid, st, info);
             if (var == 5) return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, 11, 5>(p, grid, st, info);
+            if (var == 7) return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, 11, 7>(p, grid, st, info);
             if (var == 6) return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, 11, 6>(p, grid, st, info);
 #endif
             if (var == 4) return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, 11, 4>(p, grid, st, info);
