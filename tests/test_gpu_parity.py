@@ -172,6 +172,39 @@ def test_big_engines(F, r, wname, mode, fmt):
         assert np.max(np.abs(z[k] - refz[kk])) < F64_TOL, k
 
 
+@pytest.mark.parametrize("fmt", ["c64", "u8", "c128"])
+def test_large_batch_layout_ragged(fmt):
+    """fftSize 2048 float32 batches of >= 1184 scans run the four-teams-per-CTA layout (one CTA per SM): a ragged scan count
+    (not a multiple of 4 x 148), carried state, every ingest format; everything against the oracle."""
+    F, r, gain, xres = 2048, 0.5, 19.1, 512
+    S = O.full_size(F, FS)
+    n = 4 * 148 * 2 + 37
+    win = O.window_table("hanning", F)
+    x = synth.tones_noise(n * S, seed=21, dtype=np.complex128, gate=(300000, 0.5))
+    if fmt == "u8":
+        raw = synth.to_u8_iq(x)
+        xin = synth.from_u8_iq(raw)
+    elif fmt == "c64":
+        raw = x.astype(np.complex64)
+        xin = raw.astype(np.complex128)
+    else:
+        raw = xin = x
+    per = 2 * S if fmt == "u8" else S
+    with Plan(F, S, r, win, "AVG", _ffi.in_format(raw), precision="f32") as plan:
+        first = plan.zerospan_batch(raw[:40 * per], 40, gain, xres, "MAX")                       # small batch: base layout
+        got = plan.zerospan_batch(raw[40 * per:], n - 40, gain, xres, "MAX", rows="db",
+                                  state=(first["max"], first["min"], first["avg"]))              # large batch: four teams per CTA
+        if fmt != "c128":
+            assert plan.info.cta_threads == 512 and plan.info.scans_per_cta == 4
+    lin = [O.curscan(xin[k * S:(k + 1) * S], F, r, win) for k in range(n)]
+    ref = O.zerospan(lin, gain, xres, "MAX")
+    assert np.max(np.abs(got["rows"] - ref["cur_rows"][40:])) < DB_TOL
+    assert np.array_equal(np.argmax(got["rows"], axis=1), np.argmax(ref["cur_rows"][40:], axis=1))
+    assert np.max(np.abs(got["hm_rows"] - ref["hm_rows"][40:])) < DB_TOL
+    for k in ("max", "min", "avg"):
+        assert np.max(np.abs(got[k] - ref[k])) < DB_TOL, k
+
+
 def test_cfg2_full_size_quickfullscan():
     """BASELINE cfg 2 at full size: quickFullScan 30 MHz..1.5 GHz -> 613 groups, 39 232 entries, fftSize 64, ones, r = 0.1
     (71 frames per step); 613 steps at scanRangeNonOverlap 1.0 and 1226 at the alias' default 0.5; two passes; vs the oracle."""
