@@ -245,10 +245,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     numa = bind_to_gpu_numa_node(local) if not os.environ.get("KSPEC_NO_NUMA_BIND") else None
     from kspec import _ffi
-    from kspec.engine import Plan
-    from oracle import kspec_oracle as O          # cpu_baseline leg + window table only
+    from kspec.engine import Plan                 # product path: no oracle import here (only _cpu_worker uses it)
 
-    win = O.window_table("hanning", F)
+    win = np.hanning(F)                           # the host builds the window with numpy (K:933), as kspecanal.py does
     prec = os.environ.get("KSPEC_BENCH_PRECISION", "f32")
     plan = Plan(F, S, R_NONOVERLAP, win, "AVG", _ffi.IN_C64, precision=prec, device=local)
     info = plan.info
