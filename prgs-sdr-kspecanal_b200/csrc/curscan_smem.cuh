@@ -178,7 +178,12 @@ curscan_smem_kernel(const ScanParams p) {
     if constexpr (C::TWREG) load_twiddles<T, LOG2F, LOG2P>(twl, gtw, tid);
 
     const T u8off = (T)p.u8Offset, u8scale = (T)p.u8Scale;
-    const T linScale = (T)p.linScale;
+    // AVG over the frames of a scan is the halving recurrence a_k = (a_{k-1} + m_k)/2 (data_cumu, K:137-139).  With
+    // B_k = 2^k a_k it becomes B_k = B_{k-1} + 2^(k-1) m_k: one FMA per bin and frame instead of an add and a multiply, and
+    // bit-identical (scaling by powers of two commutes with rounding); the 2^-(n-1) is folded into the per-scan scale.
+    // Only while 2^(n-2) |X| stays far from overflow.
+    const bool avgScaled = p.cumuMode == KSPEC_CUMU_AVG && p.nFrames <= (sizeof(T) == 4 ? 96 : 900);
+    const T linScale = avgScaled ? (T)ldexp(p.linScale, -(p.nFrames - 1)) : (T)p.linScale;
     const int slot = blockIdx.x * TEAMS + team;                 // stats partial owned by this team
     const int64_t scansPerIter = (int64_t)gridDim.x * TEAMS;
     const int64_t iters = (p.nScans + scansPerIter - 1) / scansPerIter;
@@ -226,6 +231,7 @@ curscan_smem_kernel(const ScanParams p) {
         const int64_t sbase = scanC * p.scanStride;
 
         T acc[P];
+        T avgW = (T)1;                                           // 2^(f-1) for frame f >= 1
         for (int f = 0; f < p.nFrames; ++f, ++g) {
             const int64_t fbase = sbase + p.frameOffs[f];
             cx<T> b[P];
@@ -263,6 +269,10 @@ curscan_smem_kernel(const ScanParams p) {
             if (f == 0 || p.cumuMode == KSPEC_CUMU_RAW) {
 #pragma unroll
                 for (int m = 0; m < P; ++m) acc[m] = kabs(b[m]);
+            } else if (avgScaled) {
+#pragma unroll
+                for (int m = 0; m < P; ++m) acc[m] = fma(kabs(b[m]), avgW, acc[m]);
+                avgW += avgW;
             } else if (p.cumuMode == KSPEC_CUMU_AVG) {
 #pragma unroll
                 for (int m = 0; m < P; ++m) acc[m] = (acc[m] + kabs(b[m])) * (T)0.5;

@@ -172,6 +172,59 @@ def test_big_engines(F, r, wname, mode, fmt):
         assert np.max(np.abs(z[k] - refz[kk])) < F64_TOL, k
 
 
+def test_fuzz_parameters():
+    """60 seeded random combinations of fftSize (power of two and not), fullSize, overlap, window, cumulate mode, ingest
+    format, precision, batch size, waterfall mode and xRes: frame offsets bit-exact, every output against the oracle."""
+    rng = np.random.default_rng(2024)
+    sizes = [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 24, 100, 384, 1000, 1536, 3000, 6000, 12000, 32768]
+    for case in range(60):
+        F = int(rng.choice(sizes))
+        pow2 = (F & (F - 1)) == 0
+        S = F * int(rng.choice([2, 3, 8]))
+        r = float(rng.choice([0.05, 0.1, 0.25, 0.3, 0.5, 0.75, 1.0, 1.5]))
+        wname = str(rng.choice(["ones", "hanning", "hamming", "kaiser"]))
+        mode = str(rng.choice(["AVG", "MAX", "MIN", "RAW"]))
+        fmt = str(rng.choice(["u8", "c64", "c128"]))
+        prec = str(rng.choice(["f32", "f64"])) if (pow2 and F <= 4096) else "auto"
+        n = int(rng.choice([1, 2, 5, 33]))
+        if F >= 6000:
+            n = min(n, 2)
+        hm_mode = str(rng.choice(["MAX", "AVG", "MIN", "RAW"]))
+        xres = O.adjust_xres(F, int(rng.choice([16, 64, 300, 512])))
+        if F % xres != 0:            # fftSize < 300 and not a multiple of xRes: the reference itself fails here (K:941-949)
+            xres = F
+        win = O.window_table(wname, F)
+        x = synth.tones_noise(n * S, seed=1000 + case, dtype=np.complex128, sigma=0.05, freqs=(211e3, -640e3, 1.07e6))
+        if fmt == "u8":
+            raw = synth.to_u8_iq(x)
+            xin = synth.from_u8_iq(raw)
+        elif fmt == "c64":
+            raw = x.astype(np.complex64)
+            xin = raw.astype(np.complex128)
+        else:
+            raw = xin = x
+        what = "case %d: F=%d S=%d r=%g %s %s %s %s n=%d hm=%s xres=%d" % (case, F, S, r, wname, mode, fmt, prec, n, hm_mode, xres)
+        offs = O.frame_offsets(F, S, r)
+        if len(offs) == 0:
+            continue
+        lin = [O.curscan(xin[k * S:(k + 1) * S], F, r, win, mode) for k in range(n)]
+        ref = O.zerospan(lin, 7.5, xres, hm_mode)
+        with Plan(F, S, r, win, mode, _ffi.in_format(raw), precision=prec) as plan:
+            assert np.array_equal(plan.frame_offsets(), offs), what
+            got = plan.zerospan_batch(raw, n, 7.5, xres, hm_mode, rows="linear")
+            db_rows = plan.zerospan_batch(raw, n, 7.5, xres, hm_mode, rows="db")["rows"]
+            f32 = plan.precision == "f32"
+        tol = DB_TOL if f32 else 1e-7
+        for k in range(n):
+            assert_db_close(got["rows"][k], lin[k], tol, what, f32=f32)
+            assert int(np.argmax(got["rows"][k])) == int(np.argmax(lin[k])), what
+        if not f32:          # float64: every derived output on every bin
+            assert np.max(np.abs(db_rows - ref["cur_rows"])) < tol, what
+            assert np.max(np.abs(got["hm_rows"] - ref["hm_rows"])) < tol, what
+            for key in ("max", "min", "avg"):
+                assert np.max(np.abs(got[key] - ref[key])) < tol, (what, key)
+
+
 @pytest.mark.parametrize("fmt", ["c64", "u8", "c128"])
 def test_large_batch_layout_ragged(fmt):
     """fftSize 2048 float32 batches of >= 1184 scans run the four-teams-per-CTA layout (one CTA per SM): a ragged scan count
