@@ -124,7 +124,9 @@ __device__ __forceinline__ float kabs(float2 a) {
 }
 __device__ __forceinline__ double kabs(double2 a) { return sqrt(a.x * a.x + a.y * a.y); }
 
-__device__ __forceinline__ float to_db(float v) { return 10.0f * log10f(v); }
+// 10*log10(v) in the float32 fast mode: MUFU.LG2 (abs error 2^-22 in log2 near 1, 2 ulp elsewhere) -> < 2e-5 dB, far inside
+// the 1e-3 dB budget, for ~20 instructions less per bin than log10f.  0 -> -inf as numpy (K:109).
+__device__ __forceinline__ float to_db(float v) { return 3.0102999566398120f * __log2f(v); }
 __device__ __forceinline__ double to_db(double v) { return 10.0 * log10(v); }
 
 template <typename T> __device__ __forceinline__ T pos_inf();
