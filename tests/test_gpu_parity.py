@@ -354,6 +354,40 @@ def test_cfg5b_full_size_bluestein_2400000():
     assert int(np.argmax(got)) == int(np.argmax(ref)) == F // 2 + 300000
 
 
+def test_cfg5b_full_fmscan_geometry():
+    """BASELINE cfg 5b at full size: fmScan 88..108 MHz -> 109.6 MHz, 9 groups, 18 steps at scanRangeNonOverlap 0.5,
+    fftSize 2 400 000 (Bluestein, M = 2^23), 21.6 M stitched entries.  numpy needs ~10 s per step here, so the FFT itself is
+    pinned by the single-scan test above and THIS test pins the rest at full size: the batched scan (clip, dB, stitch,
+    Max/Min/Avg over 21.6 M entries) must equal the oracle's stitch applied to the per-step spectra."""
+    F, r, R, gain = 2400000, 0.5, 0.5, 19.1
+    S = O.full_size(F, FS)
+    start, end, _ = O.fixup_scan_range(88e6, 108e6, FS)
+    geo = O.scan_geometry(start, end, FS, F, R)
+    num_groups, total, steps = geo
+    assert (num_groups, total, len(steps), S) == (9, 21600000, 18, 4800000)
+    win = np.ones(F)
+    base = synth.tones_noise(S, seed=55)
+    n = len(steps)
+    x = np.empty(n * S, dtype=np.complex64)
+    for s in range(n):                       # cheap per-step variation: a step-dependent tone on top of a common block
+        k = 100000 + 37000 * s
+        x[s * S:(s + 1) * S] = base * np.float32(0.5 + 0.05 * s)
+        x[s * S:(s + 1) * S] += (0.9 * np.exp(2j * np.pi * ((k * np.arange(S)) % F) / F)).astype(np.complex64)
+    st = O.scan_init_state(total, gain)
+    ref = O.scan_init_state(total, gain)
+    with Plan(F, S, r, win, "AVG", _ffi.IN_C64) as plan:
+        assert plan.path == "bluestein" and plan.n_frames == 3
+        lin = plan.zerospan_batch(x, n, gain, O.adjust_xres(F, 512), "MAX", rows="linear", want_hm=False)["rows"]
+        plan.scan_batch(x, n, [s_["i_start"] for s_ in steps], [s_["i_done"] for s_ in steps], total, O.MIN_AMP4CLIP, gain, st, 0)
+        hm = plan.plotcompress(st["avg"], O.adjust_xres(F, 512), "MAX")
+    for s in range(n):
+        assert int(np.argmax(lin[s])) == F // 2 + 100000 + 37000 * s          # the step's own tone, bin-exact
+    O.scan_pass(lin, [True] * n, geo, gain, ref, 0)
+    for k in ("cur", "max", "min", "avg"):
+        assert np.max(np.abs(st[k] - ref[k])) < 1e-9, k
+    assert hm.shape == (300,) and np.allclose(hm, O.plotcompress(ref["avg"], 300, "MAX"), atol=1e-9)
+
+
 @pytest.mark.parametrize("fmt", ["u8", "c64", "c128"])
 @pytest.mark.parametrize("prec", ["f32", "f64"])
 def test_ingest_formats(fmt, prec):
