@@ -125,6 +125,18 @@ int kspec_scan_batch(kspec_plan* plan, const void* samples, int nSteps, const ui
                      double minAmp4Clip, double gain, int baseIsRaw, int passIndex,
                      double* cur, double* max, double* min, double* avg);
 
+/* ---- the same pass sharded by frequency step over several plans / GPUs -----------------------------------
+ * kspec_scan_shard: this plan holds the captures of steps [stepBase, stepBase+nStepsLocal) of nStepsTotal; iStart has
+ * nStepsTotal entries (the global geometry).  curPartial (totalEntries) receives this shard's share of the stitched
+ * Fft.Cur -- the halving recurrence written as a weighted sum -- so that a SUM over shards (kspec_comm_allreduce_sum)
+ * equals the sequential result.  kspec_scan_stats_update then applies K:657-668 (Max/Min/Avg from the finished Fft.Cur on
+ * the bins below lastDone = iDone of the last step; bScanRangeBaseDataIsRaw is not available in sharded mode). */
+int kspec_scan_shard(kspec_plan* plan, const void* samples, int nStepsLocal, int stepBase, int nStepsTotal,
+                     const uint8_t* stepOk, const int64_t* iStart, int64_t totalEntries,
+                     double minAmp4Clip, double gain, double* curPartial);
+int kspec_scan_stats_update(kspec_plan* plan, const double* cur, int64_t totalEntries, int64_t lastDone, int passIndex,
+                            double* max, double* min, double* avg);
+
 /* ---- _data_plotcompress (K:168-202) on a float64 vector -------------------------------------------------------- */
 int kspec_plotcompress(kspec_plan* plan, const double* y, int64_t n, int xRes, int mode, double* out);
 
@@ -171,6 +183,8 @@ int kspec_comm_unique_id(char id[128]);                                  /* rank
 int kspec_comm_init(kspec_comm** out, int nRanks, int rank, const char id[128], int device);
 /* MAX on max, MIN on min, SUM on avg (pre-weighted partials of kspec_zerospan_batch); n float64 each, in place */
 int kspec_comm_allreduce_stats(kspec_comm* comm, double* max, double* min, double* avg, int64_t n);
+/* SUM over ranks of a float64 host vector, in place (the sharded stitch of kspec_scan_shard) */
+int kspec_comm_allreduce_sum(kspec_comm* comm, double* v, int64_t n);
 /* same reduction on the statistics the plan's last kspec_zerospan_batch_dev left on the device, without a host round
  * trip and ASYNCHRONOUSLY: the vectors are snapshotted onto the communicator's own stream and reduced there, so the
  * plan may start its next batch at once.  kspec_comm_join makes the plan's stream wait for the reduction and copies the

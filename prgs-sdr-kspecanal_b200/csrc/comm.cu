@@ -149,6 +149,25 @@ int kspec_comm_allreduce_stats(kspec_comm* c, double* mx, double* mn, double* av
     return KSPEC_OK;
 }
 
+int kspec_comm_allreduce_sum(kspec_comm* c, double* v, int64_t n) {
+    if (!c || !v || n < 1) { set_error("bad all-reduce arguments"); return KSPEC_ERR_ARG; }
+    CCK(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)n * 8;
+    if (c->cap < bytes) {
+        CCK(cudaStreamSynchronize(c->st));
+        if (c->buf) cudaFree(c->buf);
+        c->buf = nullptr; c->cap = 0;
+        CCK(cudaMalloc(&c->buf, bytes));
+        c->cap = bytes;
+    }
+    c->pendingN = 0;
+    CCK(cudaMemcpyAsync(c->buf, v, bytes, cudaMemcpyHostToDevice, c->st));
+    NCK(api().AllReduce(c->buf, c->buf, (size_t)n, ncclDouble, ncclSum, c->comm, c->st));
+    CCK(cudaMemcpyAsync(v, c->buf, bytes, cudaMemcpyDeviceToHost, c->st));
+    CCK(cudaStreamSynchronize(c->st));
+    return KSPEC_OK;
+}
+
 int kspec_comm_allreduce_plan(kspec_comm* c, kspec_plan* plan) {
     if (!c || !plan) { set_error("bad all-reduce arguments"); return KSPEC_ERR_ARG; }
     double* stats = nullptr;

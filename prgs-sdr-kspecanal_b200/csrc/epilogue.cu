@@ -99,6 +99,47 @@ __global__ void scan_stitch_kernel(const T* __restrict__ rows, const uint8_t* __
     }
 }
 
+// Sharded stepped scan: this rank holds the dB rows of steps [stepBase, stepBase+nLocal).  The sequential
+// stitch "first cover RAW, later covers (cur+new)/2" (K:643-650) of a bin covered by steps i0..i1 is the weighted sum
+//   cur = x_i0 * 2^-(i1-i0) + sum_{i0 < i <= i1} x_i * 2^-(i1-i+1),
+// so every rank writes the part of that sum its own steps contribute and a SUM over ranks gives Fft.Cur.
+template <typename T>
+__global__ void scan_stitch_partial_kernel(const T* __restrict__ rows, const uint8_t* __restrict__ ok, const int64_t* __restrict__ iStart,
+                                           int nSteps, int stepBase, int nLocal, int F, int64_t total, double failValue,
+                                           double* __restrict__ curPartial) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= total) return;
+    int lo = 0, hi = nSteps;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (iStart[mid] <= b) lo = mid + 1; else hi = mid; }
+    const int i1 = lo - 1;
+    lo = 0; hi = nSteps;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (iStart[mid] + F > b) hi = mid; else lo = mid + 1; }
+    const int i0 = lo;
+    double acc = 0.0;
+    if (i1 >= 0 && i0 <= i1) {
+        const int a = i0 > stepBase ? i0 : stepBase;
+        const int z = i1 < stepBase + nLocal - 1 ? i1 : stepBase + nLocal - 1;
+        for (int i = a; i <= z; ++i) {
+            const double v = (ok && !ok[i - stepBase]) ? failValue : (double)rows[(int64_t)(i - stepBase) * F + (b - iStart[i])];
+            const int sh = (i == i0) ? (i1 - i0) : (i1 - i + 1);
+            acc += ldexp(v, -sh);
+        }
+    }
+    curPartial[b] = acc;
+}
+
+// Max/Min/Avg update from a finished Fft.Cur on the slices [iStart_i, iDone_i) (K:657-668); bins past the last iDone keep
+// their state.  Used after the SUM over ranks of the sharded stitch.
+__global__ void scan_stats_update_kernel(const double* __restrict__ cur, int64_t total, int64_t lastDone, int passIndex,
+                                         double* __restrict__ mx, double* __restrict__ mn, double* __restrict__ av) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= total || b >= lastDone) return;
+    const double c = cur[b];
+    mx[b] = fmax(mx[b], c);
+    mn[b] = fmin(mn[b], c);
+    av[b] = (passIndex == 0) ? c : (av[b] + c) / 2;
+}
+
 __global__ void plotcompress_kernel(const double* __restrict__ y, int64_t g, int mode, double* __restrict__ out) {
     __shared__ double sh[256];
     const int64_t w = blockIdx.x;
@@ -319,6 +360,21 @@ void launch_plot_highs(const double* x, const double* y, int64_t n, int numMarke
 void launch_conv_same(const double* v, int64_t n, const double* taps, int m, int edge, double* out, cudaStream_t st) {
     conv_same_kernel<<<nblk(n, 256), 256, 0, st>>>(v, n, taps, m, out);
     conv_edges_kernel<<<1, 256, 0, st>>>(out, n, edge);
+}
+
+void launch_scan_stitch_partial(int prec, const void* dbRows, const uint8_t* stepOk, const int64_t* iStart, int nSteps, int stepBase,
+                                int nLocal, int F, int64_t total, double failValue, double* curPartial, cudaStream_t st) {
+    if (prec == KSPEC_PREC_F32)
+        scan_stitch_partial_kernel<float><<<nblk(total, 256), 256, 0, st>>>((const float*)dbRows, stepOk, iStart, nSteps, stepBase, nLocal, F,
+                                                                            total, failValue, curPartial);
+    else
+        scan_stitch_partial_kernel<double><<<nblk(total, 256), 256, 0, st>>>((const double*)dbRows, stepOk, iStart, nSteps, stepBase, nLocal,
+                                                                             F, total, failValue, curPartial);
+}
+
+void launch_scan_stats_update(const double* cur, int64_t total, int64_t lastDone, int passIndex, double* mx, double* mn, double* av,
+                              cudaStream_t st) {
+    scan_stats_update_kernel<<<nblk(total, 256), 256, 0, st>>>(cur, total, lastDone, passIndex, mx, mn, av);
 }
 
 void launch_plotcompress(const double* y, int64_t n, int xRes, int mode, double* out, cudaStream_t st) {

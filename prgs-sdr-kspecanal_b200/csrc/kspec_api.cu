@@ -620,6 +620,73 @@ int kspec_scan_batch(kspec_plan* pl, const void* samples, int nSteps, const uint
     return KSPEC_OK;
 }
 
+// ---- stepped scan sharded by frequency step -----------------------------------------------------------------
+int kspec_scan_shard(kspec_plan* pl, const void* samples, int nStepsLocal, int stepBase, int nStepsTotal, const uint8_t* stepOk,
+                     const int64_t* iStart, int64_t totalEntries, double minAmp4Clip, double gain, double* curPartial) {
+    if (check_plan(pl)) return KSPEC_ERR_ARG;
+    if (!samples || nStepsLocal < 1 || stepBase < 0 || stepBase + nStepsLocal > nStepsTotal || !iStart || !curPartial || totalEntries < 1) {
+        set_error("bad scan shard arguments");
+        return KSPEC_ERR_ARG;
+    }
+    for (int i = 1; i < nStepsTotal; ++i)
+        if (iStart[i] < iStart[i - 1] || iStart[i] > iStart[i - 1] + pl->F) { set_error("scanRangeNonOverlap must be in (0,1]"); return KSPEC_ERR_ARG; }
+    DeviceGuard guard(pl->device);
+    const int F = pl->F;
+    const size_t rb = real_bytes(pl->prec);
+    const size_t bytes = (size_t)nStepsLocal * pl->S * in_elem_bytes(pl->inFmt);
+    int rc;
+    if ((rc = pl->in.reserve(bytes + TAIL_PAD)) || (rc = pl->rows.reserve((size_t)nStepsLocal * F * rb))) return rc;
+    CK(cudaMemcpyAsync(pl->in.p, samples, bytes, cudaMemcpyHostToDevice, pl->st));
+    ScanParams p = base_params(pl, pl->in.p, nStepsLocal);
+    p.rowsKind = KSPEC_ROWS_DB;
+    p.rows = pl->rows.p;
+    p.dbClip = 1; p.minAmp = minAmp4Clip; p.infToZero = 1; p.gain = gain;
+    int slots = 0;
+    if ((rc = run_engine(pl, p, &slots))) return rc;
+    const size_t stBytes = (size_t)totalEntries * 8;
+    if ((rc = pl->misc.reserve(stBytes + (size_t)nStepsTotal * 8 + (size_t)nStepsLocal + 64))) return rc;
+    double* dCur = (double*)pl->misc.p;
+    int64_t* dStart = (int64_t*)(dCur + totalEntries);
+    uint8_t* dOk = (uint8_t*)(dStart + nStepsTotal);
+    CK(cudaMemcpyAsync(dStart, iStart, (size_t)nStepsTotal * 8, cudaMemcpyHostToDevice, pl->st));
+    if (stepOk) CK(cudaMemcpyAsync(dOk, stepOk, (size_t)nStepsLocal, cudaMemcpyHostToDevice, pl->st));
+    double one = 1.0 > minAmp4Clip ? 1.0 : minAmp4Clip;
+    double failValue = 10.0 * log10(one) - gain;
+    if (isinf(failValue)) failValue = 0.0;
+    launch_scan_stitch_partial(pl->prec, pl->rows.p, stepOk ? dOk : nullptr, dStart, nStepsTotal, stepBase, nStepsLocal, F, totalEntries,
+                               failValue, dCur, pl->st);
+    pl->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(curPartial, dCur, stBytes, cudaMemcpyDeviceToHost, pl->st));
+    CK(cudaStreamSynchronize(pl->st));
+    pl->haveBatch = false;
+    return KSPEC_OK;
+}
+
+int kspec_scan_stats_update(kspec_plan* pl, const double* cur, int64_t totalEntries, int64_t lastDone, int passIndex, double* mx,
+                            double* mn, double* av) {
+    if (check_plan(pl)) return KSPEC_ERR_ARG;
+    if (!cur || !mx || !mn || !av || totalEntries < 1) { set_error("bad scan stats arguments"); return KSPEC_ERR_ARG; }
+    DeviceGuard guard(pl->device);
+    const size_t stBytes = (size_t)totalEntries * 8;
+    int rc;
+    if ((rc = pl->misc.reserve(4 * stBytes))) return rc;
+    double* dCur = (double*)pl->misc.p;
+    double* dMx = dCur + totalEntries; double* dMn = dMx + totalEntries; double* dAv = dMn + totalEntries;
+    CK(cudaMemcpyAsync(dCur, cur, stBytes, cudaMemcpyHostToDevice, pl->st));
+    CK(cudaMemcpyAsync(dMx, mx, stBytes, cudaMemcpyHostToDevice, pl->st));
+    CK(cudaMemcpyAsync(dMn, mn, stBytes, cudaMemcpyHostToDevice, pl->st));
+    CK(cudaMemcpyAsync(dAv, av, stBytes, cudaMemcpyHostToDevice, pl->st));
+    launch_scan_stats_update(dCur, totalEntries, lastDone, passIndex, dMx, dMn, dAv, pl->st);
+    pl->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(mx, dMx, stBytes, cudaMemcpyDeviceToHost, pl->st));
+    CK(cudaMemcpyAsync(mn, dMn, stBytes, cudaMemcpyDeviceToHost, pl->st));
+    CK(cudaMemcpyAsync(av, dAv, stBytes, cudaMemcpyDeviceToHost, pl->st));
+    CK(cudaStreamSynchronize(pl->st));
+    return KSPEC_OK;
+}
+
 int kspec_plotcompress(kspec_plan* pl, const double* y, int64_t n, int xRes, int mode, double* out) {
     if (check_plan(pl)) return KSPEC_ERR_ARG;
     if (!y || !out || n < 1 || xRes < 1) { set_error("bad plotcompress arguments"); return KSPEC_ERR_ARG; }

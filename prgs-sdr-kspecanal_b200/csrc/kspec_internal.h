@@ -74,6 +74,10 @@ void launch_scan_stitch(int prec, const void* dbRows, const uint8_t* stepOk, con
                         double* cur, double* mx, double* mn, double* av, cudaStream_t st);
 void launch_plot_highs(const double* x, const double* y, int64_t n, int numMarkers, double delta, int64_t* idxOut, int* nOut, cudaStream_t st);
 void launch_conv_same(const double* v, int64_t n, const double* taps, int m, int edge, double* out, cudaStream_t st);
+void launch_scan_stitch_partial(int prec, const void* dbRows, const uint8_t* stepOk, const int64_t* iStart, int nSteps, int stepBase,
+                                int nLocal, int F, int64_t total, double failValue, double* curPartial, cudaStream_t st);
+void launch_scan_stats_update(const double* cur, int64_t total, int64_t lastDone, int passIndex, double* mx, double* mn, double* av,
+                              cudaStream_t st);
 void launch_plotcompress(const double* y, int64_t n, int xRes, int mode, double* out, cudaStream_t st);
 // epilogue for engines that deliver linear, un-shifted, un-normalised |X| accumulations per scan (big FFT paths)
 void launch_linear_epilogue(int prec, const ScanParams& p, const void* acc /*T[nScans][F] natural bin order*/,

@@ -56,6 +56,8 @@ SIGNATURES = {
     "kspec_zerospan_rows_batch": (C.c_int, [_P, _D, _I64, C.c_double, _D, C.c_int, C.c_int, _D, _D, _D, _D, _D, C.c_int]),
     "kspec_scan_batch": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_uint8), C.POINTER(_I64), C.POINTER(_I64), _I64, C.c_double,
                                    C.c_double, C.c_int, C.c_int, _D, _D, _D, _D]),
+    "kspec_scan_shard": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint8), C.POINTER(_I64), _I64, C.c_double, C.c_double, _D]),
+    "kspec_scan_stats_update": (C.c_int, [_P, _D, _I64, _I64, C.c_int, _D, _D, _D]),
     "kspec_plotcompress": (C.c_int, [_P, _D, _I64, C.c_int, C.c_int, _D]),
     "kspec_plot_highs": (C.c_int, [_P, _D, _D, _I64, C.c_int, C.c_double, C.POINTER(_I64), C.POINTER(C.c_int)]),
     "kspec_conv_smooth": (C.c_int, [_P, _D, _I64, _D, C.c_int, C.c_int, _D]),
@@ -78,6 +80,7 @@ SIGNATURES = {
     "kspec_comm_unique_id": (C.c_int, [C.c_char_p]),
     "kspec_comm_init": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_char_p, C.c_int]),
     "kspec_comm_allreduce_stats": (C.c_int, [_P, _D, _D, _D, _I64]),
+    "kspec_comm_allreduce_sum": (C.c_int, [_P, _D, _I64]),
     "kspec_comm_allreduce_plan": (C.c_int, [_P, _P]),
     "kspec_comm_join": (C.c_int, [_P, _P]),
     "kspec_comm_finalize": (C.c_int, [_P]),

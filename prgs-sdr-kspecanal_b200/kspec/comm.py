@@ -33,6 +33,11 @@ class Comm:
             assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
         check(_ffi.lib().kspec_comm_allreduce_stats(self._h, dptr(mx), dptr(mn), dptr(av), len(mx)))
 
+    def allreduce_sum(self, v):
+        """SUM over ranks of a float64 host vector, in place (sharded stepped scan)"""
+        assert v.dtype == np.float64 and v.flags["C_CONTIGUOUS"]
+        check(_ffi.lib().kspec_comm_allreduce_sum(self._h, dptr(v), len(v)))
+
     def allreduce_plan_stats(self, plan):
         """reduce the statistics plan.zerospan_batch_dev left on the device: asynchronous, on the communicator's own
         stream (the plan can start its next batch at once); ``join(plan)`` brings the result back into the plan"""

@@ -146,6 +146,27 @@ class Plan:
                                           dptr(state["cur"]), dptr(state["max"]), dptr(state["min"]), dptr(state["avg"])))
         return state
 
+    # -- the same pass sharded by frequency step ---------------------------------------------------------
+    def scan_shard(self, samples, n_local, step_base, i_start_all, total_entries, min_amp, gain, step_ok=None):
+        """this shard's share of the stitched Fft.Cur (float64[totalEntries]); SUM over shards = Fft.Cur"""
+        a = self._samples(samples, n_local)
+        i_start = np.ascontiguousarray(i_start_all, dtype=np.int64)
+        ok = None if step_ok is None else np.ascontiguousarray(step_ok, dtype=np.uint8)
+        out = np.empty(total_entries, dtype=np.float64)
+        check(_ffi.lib().kspec_scan_shard(self._h, vptr(a), int(n_local), int(step_base), len(i_start),
+                                          None if ok is None else ok.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                          i_start.ctypes.data_as(C.POINTER(C.c_int64)), int(total_entries), float(min_amp), float(gain),
+                                          dptr(out)))
+        return out
+
+    def scan_stats_update(self, cur, last_done, pass_index, state):
+        """K:657-668 on a finished Fft.Cur: state['max'/'min'/'avg'] updated in place on bins < last_done, state['cur'] = cur"""
+        cur = np.ascontiguousarray(cur, dtype=np.float64)
+        check(_ffi.lib().kspec_scan_stats_update(self._h, dptr(cur), len(cur), int(last_done), int(pass_index),
+                                                 dptr(state["max"]), dptr(state["min"]), dptr(state["avg"])))
+        state["cur"][:] = cur
+        return state
+
     # -- _data_plotcompress (K:168-202) ------------------------------------------------------------------
     def plotcompress(self, y, x_res, mode):
         y = np.ascontiguousarray(y, dtype=np.float64)

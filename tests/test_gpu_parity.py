@@ -512,6 +512,36 @@ def test_scan_base_is_raw_and_quarter_overlap():
     assert g["params"]["fftSize"] == 1200
 
 
+@pytest.mark.parametrize("R,n_shards", [(1.0, 3), (0.5, 2), (0.5, 5), (0.25, 4)])
+def test_scan_sharded_by_step_equals_unsharded(R, n_shards):
+    """the multi-GPU contract of the stepped scan on one device: SUM of the shards' stitch partials == Fft.Cur of the
+    unsharded pass, then Max/Min/Avg from it == the reference loop (two passes, one failed tune)"""
+    from kspec.sharding import shard_bounds
+    F, r, gain = 256, 0.1, 19.1
+    S = O.full_size(F, FS)
+    start, end = 100e6, 100e6 + 7 * FS
+    geo = O.scan_geometry(start, end, FS, F, R)
+    _, total, steps = geo
+    n = len(steps)
+    win = O.window_table("hanning", F)
+    bufs = np.concatenate([synth.step_tones(s + 7, S) for s in range(n)])
+    lin = [O.curscan(bufs[s * S:(s + 1) * S].astype(np.complex128), F, r, win) for s in range(n)]
+    ok = np.ones(n, dtype=np.uint8)
+    ok[2] = 0
+    ref = O.scan_init_state(total, gain)
+    st = O.scan_init_state(total, gain)
+    i_start = [s["i_start"] for s in steps]
+    with Plan(F, S, r, win, "AVG", precision="f64") as plan:
+        for ps in range(2):
+            O.scan_pass(lin, ok.astype(bool), geo, gain, ref, ps)
+            parts = [plan.scan_shard(bufs[a * S:b * S], b - a, a, i_start, total, O.MIN_AMP4CLIP, gain, step_ok=ok[a:b])
+                     for a, b in shard_bounds(n, n_shards) if b > a]
+            cur = np.sum(parts, axis=0)                      # what kspec_comm_allreduce_sum does over NVLink
+            plan.scan_stats_update(cur, steps[-1]["i_done"], ps, st)
+            for k in ("cur", "max", "min", "avg"):
+                assert np.max(np.abs(st[k] - ref[k])) < 1e-9, (ps, k)
+
+
 @pytest.mark.parametrize("mode", ["MAX", "AVG", "MIN", "RAW"])
 def test_plotcompress(mode):
     y = np.random.default_rng(0).normal(size=36864)

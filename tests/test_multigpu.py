@@ -47,8 +47,22 @@ def _worker(rank, world, uid_path, q):
         comm.join(plan)
         dev = plan.zerospan_fetch()
         plan.dev_free(d)
+    # stepped scan sharded by frequency step: SUM of the stitch partials over NVLink
+    from oracle import kspec_oracle as O
+    Fs, rs = 64, 0.1
+    Ss = Fs * 8
+    geo = O.scan_geometry(30e6, 30e6 + 11 * 2.4e6, 2.4e6, Fs, 0.5)
+    _, total, steps = geo
+    ns = len(steps)
+    bufs = np.concatenate([synth.step_tones(s, Ss) for s in range(ns)])
+    sa, sb = shard_bounds(ns, world)[rank]
+    with Plan(Fs, Ss, rs, np.ones(Fs), "AVG", precision="f64", device=rank) as plan:
+        cur = plan.scan_shard(bufs[sa * Ss:sb * Ss], sb - sa, sa, [s["i_start"] for s in steps], total, O.MIN_AMP4CLIP, 19.1)
+        comm.allreduce_sum(cur)
+        st = O.scan_init_state(total, 19.1)
+        plan.scan_stats_update(cur, steps[-1]["i_done"], 0, st)
     comm.close()
-    q.put((rank, out["max"], out["min"], out["avg"], dev["max"], dev["min"], dev["avg"]))
+    q.put((rank, out["max"], out["min"], out["avg"], dev["max"], dev["min"], dev["avg"], st["cur"], st["max"], st["avg"]))
 
 
 @pytest.mark.skipif(device_count() < 2, reason="needs two GPUs")
@@ -70,7 +84,14 @@ def test_two_gpu_shards_match_single_gpu(tmp_path):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    from oracle import kspec_oracle as O
+    geo = O.scan_geometry(30e6, 30e6 + 11 * 2.4e6, 2.4e6, 64, 0.5)
+    _, total, steps = geo
+    lin = [O.curscan(synth.step_tones(s, 512).astype(np.complex128), 64, 0.1, np.ones(64)) for s in range(len(steps))]
+    sref = O.scan_pass(lin, [True] * len(steps), geo, 19.1, O.scan_init_state(total, 19.1), 0)
     for r in res:
         for got in (r[1:4], r[4:7]):
             assert np.array_equal(got[0], ref["max"]) and np.array_equal(got[1], ref["min"])
             assert np.max(np.abs(got[2] - ref["avg"])) < 1e-9
+        assert np.max(np.abs(r[7] - sref["cur"])) < 1e-9 and np.max(np.abs(r[8] - sref["max"])) < 1e-9
+        assert np.max(np.abs(r[9] - sref["avg"])) < 1e-9
