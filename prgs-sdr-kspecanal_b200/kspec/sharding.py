@@ -31,3 +31,25 @@ def combine_stats(parts):
     """host-side equivalent of kspec_comm_allreduce_stats over a list of per-shard dicts (max, min, avg partial)"""
     return dict(max=np.max([p["max"] for p in parts], axis=0), min=np.min([p["min"] for p in parts], axis=0),
                 avg=np.sum([p["avg"] for p in parts], axis=0))
+
+
+def scan_cover(i_start, fft_size, total):
+    """first / last step covering every bin of a stepped scan (steps cover [iStart, iStart+F), K:622-624)"""
+    i_start = np.asarray(i_start, dtype=np.int64)
+    b = np.arange(total, dtype=np.int64)
+    i1 = np.searchsorted(i_start, b, side="right") - 1
+    i0 = np.searchsorted(i_start + fft_size, b, side="right")
+    return i0, i1
+
+
+def stitch_partial(db_rows, step_base, i_start, fft_size, total):
+    """numpy statement of kspec_scan_shard's arithmetic (host-side reference for the sharding logic, not a product path):
+    the share of steps [step_base, step_base+len(db_rows)) in the stitched Fft.Cur.  SUM over shards == K:643-650."""
+    i0, i1 = scan_cover(i_start, fft_size, total)
+    out = np.zeros(total)
+    for k, row in enumerate(db_rows):
+        i = step_base + k
+        b = np.arange(i_start[i], min(i_start[i] + fft_size, total))
+        sh = np.where(i == i0[b], i1[b] - i0[b], i1[b] - i + 1)
+        out[b] += np.ldexp(np.asarray(row, dtype=np.float64)[:len(b)], -sh.astype(np.int64))
+    return out

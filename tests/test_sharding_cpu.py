@@ -47,6 +47,24 @@ def test_combine_equals_sequential():
         assert np.allclose(got["avg"], ref["avg"], atol=1e-9)
 
 
+@pytest.mark.parametrize("R", [1.0, 0.5, 0.25])
+def test_stitch_partials_sum_to_the_sequential_stitch(R):
+    """closed-form weights of the sharded stepped scan == the reference's RAW-then-halving stitch (K:643-650)"""
+    from kspec.sharding import stitch_partial
+    F, fs = 64, 2.4e6
+    geo = O.scan_geometry(30e6, 30e6 + 6 * fs, fs, F, R)
+    _, total, steps = geo
+    n = len(steps)
+    rng = np.random.default_rng(5)
+    lin = np.abs(rng.normal(size=(n, F))) + 1e-3
+    ref = O.scan_pass(lin, [True] * n, geo, 19.1, O.scan_init_state(total, 19.1), 0)
+    db = O.log_nogain(O.clip_min(lin), 19.1, inf_to=0)
+    i_start = [s["i_start"] for s in steps]
+    for w in (1, 2, 3, 5):
+        parts = [stitch_partial(db[a:b], a, i_start, F, total) for a, b in shard_bounds(n, w) if b > a]
+        assert np.max(np.abs(np.sum(parts, axis=0) - ref["cur"])) < 1e-10, (R, w)
+
+
 def _worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
