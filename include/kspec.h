@@ -40,7 +40,11 @@ typedef enum {
 } kspec_status;
 
 /* curScanCumuMode, K:30-33, data_cumu K:124-147 */
-enum { KSPEC_CUMU_RAW = 0, KSPEC_CUMU_AVG = 1, KSPEC_CUMU_MAX = 2, KSPEC_CUMU_MIN = 3 };
+enum { KSPEC_CUMU_RAW = 0, KSPEC_CUMU_AVG = 1, KSPEC_CUMU_MAX = 2, KSPEC_CUMU_MIN = 3,
+       /* bUsePSD (K:374-384): the reference hands the scan to matplotlib's Welch PSD instead of its own loop:
+        * segments every fftSize - int(fftSize*(1-curScanNonOverlap)) samples, mean over segments of |FFT(x*w)|^2,
+        * divided by Fs*sum(w^2) with matplotlib's default Fs = 2, centred like fftshift.  float64 engines only. */
+       KSPEC_CUMU_PSD = 4 };
 /* IQ ingest formats: rtl_sdr raw interleaved uint8 I,Q (octave/load_rtlsdr.m:8-12), numpy complex64, numpy complex128 (K:335) */
 enum { KSPEC_IN_U8_IQ = 0, KSPEC_IN_C64 = 1, KSPEC_IN_C128 = 2 };
 /* arithmetic of the FFT/magnitude/cumulate chain.  AUTO = F64: within 1e-8 dB of the reference's float64 on every bin.

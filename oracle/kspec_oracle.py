@@ -111,6 +111,33 @@ def curscan(samples, fft_size, non_overlap, win, cumu_mode=CUMU_AVG):
     return np.fft.fftshift(acc)
 
 
+def psd_segments(fft_size, full_size, non_overlap):
+    """segment starts of the bUsePSD branch (K:375, K:381): noverlap = fftSize*(1-curScanNonOverlap) is a float;
+    matplotlib.mlab's segmenting truncates it (``int(noverlap)``), steps by NFFT - noverlap and keeps
+    (len(x) - noverlap) // step segments."""
+    noverlap = int(fft_size * (1 - non_overlap))
+    step = fft_size - noverlap
+    return [i * step for i in range((full_size - noverlap) // step)]
+
+
+def curscan_psd(samples, fft_size, non_overlap, win, fs=2.0):
+    """sdr_curscan with bUsePSD (K:374-384): ``plt.psd(samples, NFFT=fftSize, window=win, noverlap=noverlap)[0]``.
+
+    matplotlib is NOT under /root/reference and not installed here (parity unpinned by the reference; pinned
+    operationally against scipy.signal.welch in tests/test_oracle_golden.py).  Restated from
+    matplotlib.mlab._spectral_helper / csd / psd (3.x): complex input -> two-sided, no detrend, pad_to = NFFT,
+    per segment conj(X)*X with X = FFT(x*w), divided by Fs (default 2) and by sum(w^2) (scale_by_freq), mean over the
+    segments, real part, rolled so that frequency 0 sits at index NFFT//2 (= fftshift)."""
+    samples = np.asarray(samples, dtype=np.complex128)
+    win = np.asarray(win, dtype=np.float64)
+    acc = np.zeros(fft_size)
+    starts = psd_segments(fft_size, len(samples), non_overlap)
+    for s in starts:
+        X = np.fft.fft(samples[s:s + fft_size] * win)
+        acc += (np.conj(X) * X).real / fs / np.sum(win ** 2)
+    return np.fft.fftshift(acc / len(starts))
+
+
 # ------------------------------------------------------------------------------------------------
 # display processing (K:88-121, K:150-165)
 # ------------------------------------------------------------------------------------------------

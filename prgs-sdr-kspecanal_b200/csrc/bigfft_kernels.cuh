@@ -186,11 +186,13 @@ team_fft_acc_kernel(const RowsAccParams p, const cd* __restrict__ tw, int64_t nB
             if constexpr (C::DBUF && (C::NX & 1)) { cd* t = bufA; bufA = bufB; bufB = t; }
 #pragma unroll
             for (int m = 0; m < P; ++m) {
-                const double mag = sqrt(b[m].x * b[m].x + b[m].y * b[m].y) * p.scale;
+                double mag = sqrt(b[m].x * b[m].x + b[m].y * b[m].y) * p.scale;
+                if (p.cumuMode == KSPEC_CUMU_PSD) mag *= mag;                 // bUsePSD: power, summed (K:374-384)
                 if (f == 0 || p.cumuMode == KSPEC_CUMU_RAW) a[m] = mag;
                 else if (p.cumuMode == KSPEC_CUMU_AVG) a[m] = (a[m] + mag) / 2;
                 else if (p.cumuMode == KSPEC_CUMU_MAX) a[m] = fmax(a[m], mag);
-                else a[m] = fmin(a[m], mag);
+                else if (p.cumuMode == KSPEC_CUMU_MIN) a[m] = fmin(a[m], mag);
+                else a[m] += mag;
             }
         }
         if (valid) {
@@ -279,11 +281,13 @@ bluestein_smem_kernel(const BlueSmallParams p) {
             fft_tail<double, LOG2M, LOG2P, false, C::DBUF, L0, 0, C::NX>(b, nullptr, p.tw, bufA, bufB, tid, sync);
 #pragma unroll
             for (int m = 0; m < P; ++m) {
-                const double mag = sqrt(b[m].x * b[m].x + b[m].y * b[m].y) * invM;
+                double mag = sqrt(b[m].x * b[m].x + b[m].y * b[m].y) * invM;
+                if (p.cumuMode == KSPEC_CUMU_PSD) mag *= mag;
                 if (f == 0 || p.cumuMode == KSPEC_CUMU_RAW) acc[m] = mag;
                 else if (p.cumuMode == KSPEC_CUMU_AVG) acc[m] = (acc[m] + mag) / 2;
                 else if (p.cumuMode == KSPEC_CUMU_MAX) acc[m] = fmax(acc[m], mag);
-                else acc[m] = fmin(acc[m], mag);
+                else if (p.cumuMode == KSPEC_CUMU_MIN) acc[m] = fmin(acc[m], mag);
+                else acc[m] += mag;
             }
         }
         if (valid) {

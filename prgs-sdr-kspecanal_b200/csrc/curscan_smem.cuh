@@ -267,6 +267,17 @@ curscan_smem_kernel(const ScanParams p) {
                 fft_tail<T, LOG2F, LOG2P, C::TWREG, C::DBUF, L0, 0, 0, !C::TWSMEM>(b, twl, twtab, bufA, bufB, tid, sync);
             }
             if constexpr (C::DBUF && (C::NX & 1)) { cx<T>* t = bufA; bufA = bufB; bufB = t; }
+            if constexpr (sizeof(T) == 8) {
+                // bUsePSD (K:374-384): sum of |X|^2 over the segments; mean and 1/(Fs*sum(w^2)) are in linScale
+                if (p.cumuMode == KSPEC_CUMU_PSD) {
+#pragma unroll
+                    for (int m = 0; m < P; ++m) {
+                        const T pw = b[m].x * b[m].x + b[m].y * b[m].y;
+                        acc[m] = (f == 0) ? pw : acc[m] + pw;
+                    }
+                    continue;
+                }
+            }
             // |X| and cumulate over the frames of this scan (data_cumu, K:124-147); normalisation is applied once per scan
             if (f == 0 || p.cumuMode == KSPEC_CUMU_RAW) {
 #pragma unroll

@@ -237,7 +237,7 @@ int kspec_plan_create(kspec_plan** out, int fftSize, int64_t fullSize, double no
     *out = nullptr;
     if (fftSize < 1 || fullSize < fftSize) { set_error("fftSize %d / fullSize %lld invalid", fftSize, (long long)fullSize); return KSPEC_ERR_ARG; }
     if (!(nonOverlap > 0.0)) { set_error("curScanNonOverlap must be > 0"); return KSPEC_ERR_ARG; }
-    if (cumuMode < KSPEC_CUMU_RAW || cumuMode > KSPEC_CUMU_MIN) { set_error("unknown cumuMode %d", cumuMode); return KSPEC_ERR_ARG; }
+    if (cumuMode < KSPEC_CUMU_RAW || cumuMode > KSPEC_CUMU_PSD) { set_error("unknown cumuMode %d", cumuMode); return KSPEC_ERR_ARG; }
     if (inFmt < KSPEC_IN_U8_IQ || inFmt > KSPEC_IN_C128) { set_error("unknown ingest format %d", inFmt); return KSPEC_ERR_ARG; }
     if (precision < KSPEC_PREC_AUTO || precision > KSPEC_PREC_F64) { set_error("unknown precision %d", precision); return KSPEC_ERR_ARG; }
     int ndev = 0;
@@ -255,6 +255,7 @@ int kspec_plan_create(kspec_plan** out, int fftSize, int64_t fullSize, double no
     const bool pow2 = (fftSize & (fftSize - 1)) == 0;
     if (pow2) { int l = 0; while ((1 << l) < fftSize) ++l; pl->log2F = l; }
     if (precision == KSPEC_PREC_AUTO) precision = KSPEC_PREC_F64;     // parity first; F32 is the explicit fast mode
+    if (cumuMode == KSPEC_CUMU_PSD && precision != KSPEC_PREC_F64) { delete pl; set_error("bUsePSD (KSPEC_CUMU_PSD) runs on the float64 engines only"); return KSPEC_ERR_ARG; }
     pl->prec = precision;
     const int smemMax = precision == KSPEC_PREC_F32 ? SMEM_MAX_LOG2F_F32 : SMEM_MAX_LOG2F_F64;
     if (pow2 && pl->log2F >= SMEM_MIN_LOG2F && pl->log2F <= smemMax) pl->path = KSPEC_PATH_SMEM;
@@ -262,11 +263,21 @@ int kspec_plan_create(kspec_plan** out, int fftSize, int64_t fullSize, double no
     else pl->path = KSPEC_PATH_BLUESTEIN;
 
     // frame offsets: int(i*F*r) with the product evaluated left to right in float64 (K:368, K:386-390)
-    const int64_t nLoops = (int64_t)((double)fullSize / ((double)fftSize * nonOverlap));
-    for (int64_t i = 0; i < nLoops; ++i) {
-        const int64_t start = (int64_t)(((double)i * (double)fftSize) * nonOverlap);
-        if (start + fftSize > fullSize) break;
-        pl->offs.push_back(start);
+    if (cumuMode == KSPEC_CUMU_PSD) {
+        // K:375, K:381: noverlap = fftSize*(1-curScanNonOverlap) (float64), truncated by matplotlib's segmenting; a segment
+        // every fftSize - noverlap samples, (fullSize - noverlap) // step segments
+        const int64_t nover = (int64_t)((double)fftSize * (1.0 - nonOverlap));
+        const int64_t step = (int64_t)fftSize - nover;
+        if (nover < 0 || step < 1) { delete pl; set_error("bUsePSD: curScanNonOverlap %g leaves no segment step", nonOverlap); return KSPEC_ERR_ARG; }
+        const int64_t nSeg = (fullSize - nover) / step;
+        for (int64_t i = 0; i < nSeg; ++i) pl->offs.push_back(i * step);
+    } else {
+        const int64_t nLoops = (int64_t)((double)fullSize / ((double)fftSize * nonOverlap));
+        for (int64_t i = 0; i < nLoops; ++i) {
+            const int64_t start = (int64_t)(((double)i * (double)fftSize) * nonOverlap);
+            if (start + fftSize > fullSize) break;
+            pl->offs.push_back(start);
+        }
     }
     if (pl->offs.empty()) { delete pl; set_error("no complete frame fits (fullSize %lld, fftSize %d, nonOverlap %g)", (long long)fullSize, fftSize, nonOverlap); return KSPEC_ERR_ARG; }
     double sum = 0.0;                                        // np.sum is pairwise; plain summation differs by < 1e-13 relative
@@ -278,6 +289,14 @@ int kspec_plan_create(kspec_plan** out, int fftSize, int64_t fullSize, double no
     }
     pl->winAdj = (double)fftSize / sum;
     pl->linScale = pl->winAdj * 2.0 / (double)fftSize;
+    if (cumuMode == KSPEC_CUMU_PSD) {
+        // mean over the segments of |X|^2 / (Fs * sum(w^2)), Fs = 2 (matplotlib default; the reference passes none, K:381)
+        std::vector<double> t(fftSize);
+        for (int i = 0; i < fftSize; ++i) t[i] = window[i] * window[i];
+        size_t n = t.size();
+        while (n > 1) { size_t h = n / 2; for (size_t i = 0; i < h; ++i) t[i] = t[2 * i] + t[2 * i + 1]; if (n & 1) { t[h] = t[n - 1]; n = h + 1; } else n = h; }
+        pl->linScale = 1.0 / ((double)pl->offs.size() * 2.0 * t[0]);
+    }
 
     DeviceGuard guard(device);
     auto fail = [&](int rc) { kspec_plan_destroy(pl); return rc; };

@@ -12,7 +12,7 @@ import numpy as np
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libkspec.so")
 
 OK = 0
-CUMU = {"RAW": 0, "AVG": 1, "MAX": 2, "MIN": 3}
+CUMU = {"RAW": 0, "AVG": 1, "MAX": 2, "MIN": 3, "PSD": 4}
 IN_U8_IQ, IN_C64, IN_C128 = 0, 1, 2
 PREC = {"auto": 0, "f32": 1, "f64": 2}
 PREC_NAME = {1: "f32", 2: "f64"}

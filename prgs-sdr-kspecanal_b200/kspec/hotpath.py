@@ -92,7 +92,9 @@ def _fixupfreqs_scanrange(d):
 # plan cache: one GPU plan per (shape, window, mode, ingest format)
 # ------------------------------------------------------------------------------------------------------
 def _plan(d, in_fmt=_ffi.IN_C128):
-    key = (int(d["fftSize"]), int(d["fullSize"]), float(d["curScanNonOverlap"]), str(d["curScanCumuMode"]).upper(),
+    # bUsePSD (K:374-384) replaces the cumulate loop by a Welch PSD of the same scan: its own cumulate mode in the plan
+    cumu = "PSD" if d.get("bUsePSD") else str(d["curScanCumuMode"]).upper()
+    key = (int(d["fftSize"]), int(d["fullSize"]), float(d["curScanNonOverlap"]), cumu,
            d["window"], in_fmt, d.get("kspec.precision", "auto"), int(d.get("kspec.device", 0)))
     cache = d.setdefault("kspec.plans", {})
     if key not in cache:

@@ -621,3 +621,42 @@ def test_full_size_cfg1_properties():
         assert np.max(np.abs(a["rows"][s] - ref)) < DB_TOL
         assert int(np.argmax(a["rows"][s])) == int(np.argmax(ref)) == F // 2 + 256
     assert a["hm_rows"].shape == (n, xres)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# bUsePSD (K:374-384): Welch PSD through the same engines (row N4 of SURVEY 8f)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("F,r,wname,fmt,path", [
+    (2048, 0.5, "hanning", "c64", "smem"), (2048, 0.1, "kaiser", "u8", "smem"), (64, 0.1, "ones", "c128", "smem"),
+    (8192, 0.25, "hamming", "c64", "smem"), (16384, 0.1, "hanning", "c128", "fourstep"), (1 << 17, 0.5, "ones", "u8", "fourstep"),
+    (1000, 0.25, "hamming", "c64", "bluestein"), (5000, 0.1, "kaiser", "c128", "bluestein"), (48000, 0.5, "hanning", "u8", "bluestein"),
+])
+def test_use_psd_mode(F, r, wname, fmt, path):
+    S = O.full_size(F, FS)
+    win = O.window_table(wname, F)
+    x = synth.tones_noise(S * 2, seed=F % 89, dtype=np.complex128, sigma=0.02)
+    if fmt == "u8":
+        raw = synth.to_u8_iq(x)
+        xin = synth.from_u8_iq(raw)
+    elif fmt == "c64":
+        raw = x.astype(np.complex64)
+        xin = raw.astype(np.complex128)
+    else:
+        raw = xin = x
+    ref = [O.curscan_psd(xin[k * S:(k + 1) * S], F, r, win) for k in range(2)]
+    with Plan(F, S, r, win, "PSD", _ffi.in_format(raw)) as plan:
+        assert plan.precision == "f64" and plan.path == path
+        assert np.array_equal(plan.frame_offsets(), O.psd_segments(F, S, r))       # segment starts: bit-exact
+        got = plan.curscan(raw[:S * (2 if fmt == "u8" else 1)])
+        z = plan.zerospan_batch(raw, 2, 19.1, O.adjust_xres(F, 512), "MAX", rows="db")
+    assert np.max(np.abs(db(got) - db(ref[0]))) < F64_TOL
+    assert int(np.argmax(got)) == int(np.argmax(ref[0]))
+    refz = O.zerospan(ref, 19.1, O.adjust_xres(F, 512), "MAX")
+    for k, kk in (("rows", "cur_rows"), ("hm_rows", "hm_rows"), ("max", "max"), ("min", "min"), ("avg", "avg")):
+        assert np.max(np.abs(z[k] - refz[kk])) < F64_TOL, k
+
+
+def test_use_psd_needs_float64():
+    from kspec.engine import KspecError
+    with pytest.raises(KspecError):
+        Plan(2048, 16384, 0.5, np.hanning(2048), "PSD", _ffi.IN_C64, precision="f32")

@@ -155,3 +155,16 @@ def test_unknown_modes_quit_like_the_reference():
         H._data_plotcompress(d, np.zeros(64), "MIN")          # documented but unreachable in the reference (K:188, K:202)
     with pytest.raises(KeyError):
         _d(fftSize=64, window="rectangle")                    # K:936: only ones/hanning/hamming/kaiser exist
+
+
+def test_sdr_curscan_with_use_psd():
+    """bUsePSD true (K:374-384): the seam returns the Welch PSD of the scan instead of the cumulated magnitudes"""
+    from oracle import kspec_oracle as O
+    x = synth.tones_noise(16384 * 2, seed=21, dtype=np.complex128)
+    d = _d(fftSize=2048, window="hanning", curScanNonOverlap=0.1, bUsePSD=True)
+    d["sdr"] = synth.ArrayRtlSdr(x)
+    for k in range(2):
+        out = H.sdr_curscan(d)
+        ref = O.curscan_psd(x[k * 16384:(k + 1) * 16384], 2048, 0.1, d["theWin"])
+        assert out.shape == (2048,) and np.max(np.abs(10 * np.log10(out) - 10 * np.log10(ref))) < TOL
+    H.close_plans(d)

@@ -140,3 +140,23 @@ def test_known_answers():
     assert len(O.frame_offsets(8192, 65536, 0.25)) == 29
     assert len(O.frame_offsets(2 ** 21, 2 ** 22, 0.1)) == 11
     assert O.sdr_read_plan(4800000)[-1] == (131072, 81408)
+
+
+@pytest.mark.parametrize("F,S,r,wname", [(2048, 16384, 0.5, "hanning"), (2048, 16384, 0.1, "kaiser"), (64, 512, 0.1, "ones"),
+                                           (1000, 8000, 0.25, "hamming")])
+def test_psd_restatement_against_scipy_welch(F, S, r, wname):
+    """bUsePSD (K:374-384) calls matplotlib, which is neither in the reference tree nor installed: the oracle's
+    restatement of mlab.psd is pinned against scipy.signal.welch, an independent implementation of the same estimate
+    (density scaling, Fs = 2, no detrend, two-sided, mean over segments)."""
+    signal = pytest.importorskip("scipy.signal")
+    win = O.window_table(wname, F)
+    x = synth.tones_noise(S, seed=11).astype(np.complex128)
+    noverlap = int(F * (1 - r))
+    _, pxx = signal.welch(x, fs=2.0, window=win, nperseg=F, noverlap=noverlap, nfft=F, detrend=False,
+                          return_onesided=False, scaling="density", average="mean")
+    got = O.curscan_psd(x, F, r, win)
+    assert len(O.psd_segments(F, S, r)) == (S - noverlap) // (F - noverlap)
+    assert np.allclose(got, np.fft.fftshift(pxx), rtol=1e-12, atol=0)
+    # Parseval: integrating the density over the two-sided band gives the windowed mean power
+    k = int(np.argmax(got))
+    assert k == int(np.argmax(O.curscan(x, F, r, win)))           # same strongest bin as the magnitude path
