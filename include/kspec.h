@@ -54,7 +54,7 @@ enum { KSPEC_PREC_AUTO = 0, KSPEC_PREC_F32 = 1, KSPEC_PREC_F64 = 2 };
 /* pltCompress / pltCompressHM, K:25-29, _data_plotcompress K:168-202 (MIN: documented, unreachable in the reference) */
 enum { KSPEC_COMPRESS_RAW = 0, KSPEC_COMPRESS_MAX = 1, KSPEC_COMPRESS_AVG = 2, KSPEC_COMPRESS_MIN = 3 };
 /* which FFT engine a plan resolved to (kspec_plan_info) */
-enum { KSPEC_PATH_SMEM = 0, KSPEC_PATH_FOURSTEP = 1, KSPEC_PATH_BLUESTEIN = 2 };
+enum { KSPEC_PATH_SMEM = 0, KSPEC_PATH_FOURSTEP = 1, KSPEC_PATH_BLUESTEIN = 2, KSPEC_PATH_MIXEDRADIX = 3 };
 /* kind of per-scan rows a batch emits */
 enum { KSPEC_ROWS_NONE = 0, KSPEC_ROWS_LINEAR = 1, KSPEC_ROWS_DB = 2 };
 

@@ -69,6 +69,7 @@ struct kspec_plan {
     SmemKernelInfo kiMulti{};     // multi-team variant (ctasPerSm == 0: not available for this shape)
     int64_t convSize = 0;
     BigFft* big = nullptr;
+    MixedRadix* mixed = nullptr;
     int64_t launches = 0;
     // event pairs around the most recent engine launches (bench: per-kernel duration for the roofline)
     static constexpr int KT = 64;
@@ -169,10 +170,16 @@ int run_engine(kspec_plan* pl, ScanParams& p, int* slotsOut) {
         p.wsMax = pl->wsMax.p;
         p.wsMin = pl->wsMin.p;
     }
-    rc = bigfft_run(pl->big, p.samples, pl->S, p.nScans, pl->offs.data(), (int)pl->offs.size(), pl->cumu, pl->acc.p, &pl->launches);
-    if (rc) return rc;
-    p.accL1 = bigfft_acc_l1(pl->big);
-    p.accL2 = bigfft_acc_l2(pl->big);
+    if (pl->mixed) {
+        rc = mixedradix_run(pl->mixed, p.samples, pl->S, p.nScans, pl->offs.data(), (int)pl->offs.size(), pl->cumu, pl->acc.p, &pl->launches);
+        if (rc) return rc;
+        p.accL1 = p.accL2 = 0;
+    } else {
+        rc = bigfft_run(pl->big, p.samples, pl->S, p.nScans, pl->offs.data(), (int)pl->offs.size(), pl->cumu, pl->acc.p, &pl->launches);
+        if (rc) return rc;
+        p.accL1 = bigfft_acc_l1(pl->big);
+        p.accL2 = bigfft_acc_l2(pl->big);
+    }
     launch_linear_epilogue(pl->prec, p, pl->acc.p, pl->F, 1, pl->st);
     pl->launches += p.hm ? 2 : 1;
     *slotsOut = 1;
@@ -261,6 +268,13 @@ int kspec_plan_create(kspec_plan** out, int fftSize, int64_t fullSize, double no
     if (pow2 && pl->log2F >= SMEM_MIN_LOG2F && pl->log2F <= smemMax) pl->path = KSPEC_PATH_SMEM;
     else if (pow2 && pl->log2F > smemMax) pl->path = KSPEC_PATH_FOURSTEP;
     else pl->path = KSPEC_PATH_BLUESTEIN;
+    {   // 7-smooth lengths beyond the one-kernel Bluestein range: a direct two-pass mixed-radix transform (what numpy does at
+        // K:391 for such sizes).  KSPEC_FORCE_BLUESTEIN=1 keeps the chirp-z engine (BASELINE cfg-5 names it).
+        int n1 = 0, n2 = 0;
+        const char* fb = getenv("KSPEC_FORCE_BLUESTEIN");
+        if (pl->path == KSPEC_PATH_BLUESTEIN && fftSize > 4096 && !(fb && fb[0] == '1') && mixedradix_split(fftSize, &n1, &n2))
+            pl->path = KSPEC_PATH_MIXEDRADIX;
+    }
 
     // frame offsets: int(i*F*r) with the product evaluated left to right in float64 (K:368, K:386-390)
     if (cumuMode == KSPEC_CUMU_PSD) {
@@ -353,6 +367,10 @@ int kspec_plan_create(kspec_plan** out, int fftSize, int64_t fullSize, double no
         if (launch_smem(pl, SMEM_VARIANT_MULTI, dummy, 0, &pl->kiMulti) != 0) { cudaGetLastError(); pl->kiMulti = SmemKernelInfo{}; }
         if (launch_smem(pl, SMEM_VARIANT_BASE, dummy, 0, &pl->ki) != 0) { set_error("kernel attribute query failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(KSPEC_ERR_CUDA); }
         if (pl->ki.ctasPerSm < 1) { set_error("fused kernel for fftSize %d does not fit on this device", fftSize); return fail(KSPEC_ERR_UNSUPPORTED); }
+    } else if (pl->path == KSPEC_PATH_MIXEDRADIX) {
+        char err[256] = "";
+        pl->mixed = mixedradix_create(precision, inFmt, fftSize, window, u8_offset, u8_scale, pl->st, err, sizeof(err));
+        if (!pl->mixed) { set_error("mixed-radix engine: %s", err); return fail(KSPEC_ERR_UNSUPPORTED); }
     } else {
         char err[256] = "";
         pl->big = bigfft_create(precision, inFmt, fftSize, pl->path, &pl->convSize, window, u8_offset, u8_scale, pl->st, err, sizeof(err));
@@ -368,6 +386,7 @@ int kspec_plan_destroy(kspec_plan* pl) {
     DeviceGuard guard(pl->device);
     if (pl->st) cudaStreamSynchronize(pl->st);
     if (pl->big) bigfft_destroy(pl->big);
+    if (pl->mixed) mixedradix_destroy(pl->mixed);
     for (DevBuf* b : {&pl->in, &pl->rows, &pl->hm, &pl->wsMax, &pl->wsMin, &pl->avgRows, &pl->adj, &pl->adj64, &pl->carry, &pl->stats,
                       &pl->wide, &pl->acc, &pl->l2, &pl->misc}) b->release();
     if (pl->dOffs) cudaFree(pl->dOffs);

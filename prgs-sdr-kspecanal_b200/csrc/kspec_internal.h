@@ -95,6 +95,16 @@ int bigfft_run(BigFft*, const void* samples, int64_t scanStride, int64_t nScans,
 int bigfft_acc_l1(const BigFft*);
 int bigfft_acc_l2(const BigFft*);
 
+// ---- mixedradix.cu ---------------------------------------------------------------------------------------------------
+struct MixedRadix;   // two-pass engine for 7-smooth, non power-of-two frame lengths (2.4e6 = 2^8.3.5^5)
+bool mixedradix_split(int64_t F, int* n1, int* n2);
+MixedRadix* mixedradix_create(int prec, int inFmt, int64_t F, const double* window, double u8off, double u8scale, cudaStream_t st,
+                              char* err, size_t errLen);
+void mixedradix_destroy(MixedRadix*);
+// acc[scan][bin] (float64, natural bin order)
+int mixedradix_run(MixedRadix*, const void* samples, int64_t scanStride, int64_t nScans, const int64_t* frameOffs, int nFrames,
+                   int cumuMode, void* acc, int64_t* launches);
+
 // float64 (re, im) pairs of the linearised twiddle table of an F = 2^log2F transform with the kernels' stage schedule
 std::vector<double> host_lin_twiddles(int log2F);
 

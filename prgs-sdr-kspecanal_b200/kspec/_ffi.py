@@ -17,7 +17,7 @@ IN_U8_IQ, IN_C64, IN_C128 = 0, 1, 2
 PREC = {"auto": 0, "f32": 1, "f64": 2}
 PREC_NAME = {1: "f32", 2: "f64"}
 COMPRESS = {"RAW": 0, "MAX": 1, "AVG": 2, "MIN": 3}
-PATH_NAME = {0: "smem", 1: "fourstep", 2: "bluestein"}
+PATH_NAME = {0: "smem", 1: "fourstep", 2: "bluestein", 3: "mixedradix"}
 ROWS_NONE, ROWS_LINEAR, ROWS_DB = 0, 1, 2
 
 

@@ -135,6 +135,17 @@ def test_curscan_all_sizes(log2f, prec):
     assert int(np.argmax(got)) == int(np.argmax(ref))
 
 
+def expected_big_path(F):
+    """power of two -> four-step; 7-smooth above the fused Bluestein kernel's range -> mixed radix; the rest -> Bluestein"""
+    if (F & (F - 1)) == 0 and F > 8:
+        return "fourstep"
+    rest = F
+    for q in (2, 3, 5, 7):
+        while rest % q == 0:
+            rest //= q
+    return "mixedradix" if rest == 1 and F > 4096 else "bluestein"
+
+
 @pytest.mark.parametrize("F,r,wname,mode,fmt", [
     (16384, 0.5, "hanning", "AVG", "c64"),          # float64 frames above 8192: four-step engine (2^14 = 128 x 128)
     (65536, 0.1, "ones", "MAX", "c128"),
@@ -143,8 +154,13 @@ def test_curscan_all_sizes(log2f, prec):
     (1001, 0.5, "hamming", "MIN", "c128"),          # odd length
     (8, 0.5, "ones", "AVG", "c64"),                 # below the fused kernel's minimum
     (3, 1.0, "ones", "MAX", "c64"),
-    (5000, 0.25, "kaiser", "RAW", "u8"),            # Bluestein, M = 16384 (multi-pass)
-    (48000, 0.5, "hanning", "AVG", "c64"),          # Bluestein, M = 2^17
+    (5001, 0.25, "kaiser", "RAW", "u8"),            # Bluestein, M = 16384 (multi-pass): 5001 = 3 x 1667
+    (48001, 0.5, "hanning", "AVG", "c64"),          # Bluestein, M = 2^17: 48001 = 23 x 2087
+    (5000, 0.25, "kaiser", "RAW", "u8"),            # 7-smooth lengths above 4096: two-pass mixed radix, 50 x 100
+    (48000, 0.5, "hanning", "AVG", "c64"),          # 200 x 240
+    (6174, 0.1, "hamming", "MAX", "c128"),          # 2.3^2.7^3 = 63 x 98: radix 7 and 3
+    (30375, 0.5, "ones", "MIN", "c64"),             # 3^5.5^3 = 135 x 225: odd
+    (1 << 13 | 1 << 12, 0.5, "hanning", "AVG", "u8"),   # 12288 = 3.2^12 = 96 x 128: radix 4 / 2 lines
 ])
 def test_big_engines(F, r, wname, mode, fmt):
     S = O.full_size(F, FS)
@@ -161,7 +177,7 @@ def test_big_engines(F, r, wname, mode, fmt):
     ref = O.curscan(xin, F, r, win, mode)
     with Plan(F, S, r, win, mode, _ffi.in_format(raw)) as plan:
         assert plan.precision == "f64"
-        assert plan.path == ("fourstep" if (F & (F - 1)) == 0 and F > 8 else "bluestein")
+        assert plan.path == expected_big_path(F)
         assert np.array_equal(plan.frame_offsets(), O.frame_offsets(F, S, r))
         got = plan.curscan(raw)
         z = plan.zerospan_batch(np.concatenate([raw, raw]), 2, 19.1, O.adjust_xres(F, 512), "MAX", rows="db")
@@ -339,8 +355,12 @@ def test_cfg4_full_size_two_to_the_21():
     assert int(np.argmax(got)) == int(np.argmax(ref)) == F // 2 + int(round(300e3 * F / FS))
 
 
-def test_cfg5b_full_size_bluestein_2400000():
-    """BASELINE cfg 5b: fftSize 2 400 000 (= one second at 2.4 MS/s), Bluestein with M = 2^23"""
+@pytest.mark.parametrize("engine", ["mixedradix", "bluestein"])
+def test_cfg5b_full_size_2400000(engine, monkeypatch):
+    """BASELINE cfg 5b: fftSize 2 400 000 (= one second at 2.4 MS/s): the two-pass mixed-radix engine (1500 x 1600,
+    default) and the Bluestein engine BASELINE names (M = 2^23, KSPEC_FORCE_BLUESTEIN=1)"""
+    if engine == "bluestein":
+        monkeypatch.setenv("KSPEC_FORCE_BLUESTEIN", "1")
     F, r = 2400000, 0.5
     S = O.full_size(F, FS)
     assert S == 4800000
@@ -348,15 +368,15 @@ def test_cfg5b_full_size_bluestein_2400000():
     x = synth.tones_noise(S, seed=5)
     ref = O.curscan(x.astype(np.complex128), F, r, win, "AVG")
     with Plan(F, S, r, win, "AVG", _ffi.IN_C64) as plan:
-        assert plan.path == "bluestein" and plan.info.conv_size == 1 << 23
+        assert plan.path == engine and plan.info.conv_size == (1 << 23 if engine == "bluestein" else 0)
         got = plan.curscan(x)
-    assert_db_close(got, ref, 1e-6, "2.4e6")
+    assert_db_close(got, ref, 1e-6 if engine == "bluestein" else F64_TOL, "2.4e6")
     assert int(np.argmax(got)) == int(np.argmax(ref)) == F // 2 + 300000
 
 
 def test_cfg5b_full_fmscan_geometry():
     """BASELINE cfg 5b at full size: fmScan 88..108 MHz -> 109.6 MHz, 9 groups, 18 steps at scanRangeNonOverlap 0.5,
-    fftSize 2 400 000 (Bluestein, M = 2^23), 21.6 M stitched entries.  numpy needs ~10 s per step here, so the FFT itself is
+    fftSize 2 400 000 (mixed radix 1500 x 1600), 21.6 M stitched entries.  numpy needs ~10 s per step here, so the FFT itself is
     pinned by the single-scan test above and THIS test pins the rest at full size: the batched scan (clip, dB, stitch,
     Max/Min/Avg over 21.6 M entries) must equal the oracle's stitch applied to the per-step spectra."""
     F, r, R, gain = 2400000, 0.5, 0.5, 19.1
@@ -376,7 +396,7 @@ def test_cfg5b_full_fmscan_geometry():
     st = O.scan_init_state(total, gain)
     ref = O.scan_init_state(total, gain)
     with Plan(F, S, r, win, "AVG", _ffi.IN_C64) as plan:
-        assert plan.path == "bluestein" and plan.n_frames == 3
+        assert plan.path == "mixedradix" and plan.n_frames == 3
         lin = plan.zerospan_batch(x, n, gain, O.adjust_xres(F, 512), "MAX", rows="linear", want_hm=False)["rows"]
         plan.scan_batch(x, n, [s_["i_start"] for s_ in steps], [s_["i_done"] for s_ in steps], total, O.MIN_AMP4CLIP, gain, st, 0)
         hm = plan.plotcompress(st["avg"], O.adjust_xres(F, 512), "MAX")
@@ -629,7 +649,7 @@ def test_full_size_cfg1_properties():
 @pytest.mark.parametrize("F,r,wname,fmt,path", [
     (2048, 0.5, "hanning", "c64", "smem"), (2048, 0.1, "kaiser", "u8", "smem"), (64, 0.1, "ones", "c128", "smem"),
     (8192, 0.25, "hamming", "c64", "smem"), (16384, 0.1, "hanning", "c128", "fourstep"), (1 << 17, 0.5, "ones", "u8", "fourstep"),
-    (1000, 0.25, "hamming", "c64", "bluestein"), (5000, 0.1, "kaiser", "c128", "bluestein"), (48000, 0.5, "hanning", "u8", "bluestein"),
+    (1000, 0.25, "hamming", "c64", "bluestein"), (5001, 0.1, "kaiser", "c128", "bluestein"), (48000, 0.5, "hanning", "u8", "mixedradix"),
 ])
 def test_use_psd_mode(F, r, wname, fmt, path):
     S = O.full_size(F, FS)
