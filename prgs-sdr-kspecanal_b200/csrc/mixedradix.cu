@@ -19,35 +19,42 @@
 namespace kspec {
 
 constexpr int MR_MAX_STAGES = 16;
-constexpr int MR_THREADS = 256;
+constexpr int MR_THREADS = 512;                   // default CTA (64 registers, two CTAs per SM); KSPEC_MR_THREADS=256 for tuning
 constexpr int MR_MAX_LINE = 6144;                 // longest line: one buffer pair of 2 x 96 KB
-constexpr int MR_TILE_ELEMS = 6144;               // TC * L <= this (elements per buffer)
-constexpr int MR_TILE_TARGET = 3200;              // default tile: two CTAs (2 x 100 KB) per SM so loads overlap butterflies
-constexpr int MR_MAXA_BIG = (MR_TILE_ELEMS + MR_THREADS - 1) / MR_THREADS;      // accumulators per thread, largest tile
-constexpr int MR_MAXA_STD = (MR_TILE_TARGET + MR_THREADS - 1) / MR_THREADS;     // ... default tile (two CTAs per SM)
+constexpr int MR_SMEM_BIG = 220 * 1024;           // one CTA per SM: long lines
+constexpr int MR_SMEM_STD = 112 * 1024;           // default tile: two CTAs per SM, so one CTA's loads overlap the other's butterflies
+constexpr int MR_TW_LO_BITS = 10;                 // inter-pass twiddle W_F^t = hi[t >> 10] * lo[t & 1023]: both tables cache-resident
+constexpr int mr_maxa(int smem, int nt) { return (smem / 32 + nt - 1) / nt; }       // accumulators per thread for a tile
 
 struct MrSched {
     int L;                        // line length
-    int TC;                       // lines per tile
+    int TC, lTC;                  // lines per tile (power of two) and its log2
     int nStages;
+    int tabN;                     // twiddle entries kept in shared memory: exp(-2 pi i t/L), t < L / (smallest twiddled radix)
+    uint32_t mL;                  // magic reciprocal of L
     int radix[MR_MAX_STAGES];
+    uint32_t mNs[MR_MAX_STAGES];  // magic reciprocals of the stage's sub-transform length Ns and butterfly count L/R
+    uint32_t mNb[MR_MAX_STAGES];
 };
 
 namespace {
+
+// n / d for n * d < 2^32 with m = ceil(2^32 / d), d >= 2
+__device__ __forceinline__ int mr_div(int n, uint32_t m) { return (int)__umulhi((uint32_t)n, m); }
 
 __device__ __forceinline__ cd cadd(cd a, cd b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ cd csub(cd a, cd b) { return make_double2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ cd cscale(cd a, double s) { return make_double2(a.x * s, a.y * s); }
 __device__ __forceinline__ cd mul_mi(cd a) { return make_double2(a.y, -a.x); }      // a * (-i)
 
-template <int R> __device__ __forceinline__ void mr_dft(cd* v, const cd* __restrict__ tab, int L);
+template <int R> __device__ __forceinline__ void mr_dft(cd* v);
 
-template <> __device__ __forceinline__ void mr_dft<2>(cd* v, const cd*, int) {
+template <> __device__ __forceinline__ void mr_dft<2>(cd* v) {
     const cd a = v[0];
     v[0] = cadd(a, v[1]);
     v[1] = csub(a, v[1]);
 }
-template <> __device__ __forceinline__ void mr_dft<3>(cd* v, const cd*, int) {
+template <> __device__ __forceinline__ void mr_dft<3>(cd* v) {
     const cd t = cadd(v[1], v[2]);
     const cd m = make_double2(v[0].x - 0.5 * t.x, v[0].y - 0.5 * t.y);
     const cd s = mul_mi(cscale(csub(v[1], v[2]), 0.86602540378443864676));      // -i sin(pi/3) (v1 - v2)
@@ -55,14 +62,14 @@ template <> __device__ __forceinline__ void mr_dft<3>(cd* v, const cd*, int) {
     v[1] = cadd(m, s);
     v[2] = csub(m, s);
 }
-template <> __device__ __forceinline__ void mr_dft<4>(cd* v, const cd*, int) {
+template <> __device__ __forceinline__ void mr_dft<4>(cd* v) {
     const cd a = cadd(v[0], v[2]), b = csub(v[0], v[2]), c = cadd(v[1], v[3]), d = mul_mi(csub(v[1], v[3]));
     v[0] = cadd(a, c);
     v[1] = cadd(b, d);
     v[2] = csub(a, c);
     v[3] = csub(b, d);
 }
-template <> __device__ __forceinline__ void mr_dft<5>(cd* v, const cd*, int) {
+template <> __device__ __forceinline__ void mr_dft<5>(cd* v) {
     constexpr double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;      // cos(2pi/5), cos(4pi/5)
     constexpr double s1 = 0.95105651629515357212, s2 = 0.58778525229247312917;       // sin(2pi/5), sin(4pi/5)
     const cd a1 = cadd(v[1], v[4]), a2 = cadd(v[2], v[3]), b1 = csub(v[1], v[4]), b2 = csub(v[2], v[3]);
@@ -76,63 +83,72 @@ template <> __device__ __forceinline__ void mr_dft<5>(cd* v, const cd*, int) {
     v[2] = cadd(p2, q2);
     v[3] = csub(p2, q2);
 }
-template <> __device__ __forceinline__ void mr_dft<7>(cd* v, const cd* __restrict__ tab, int L) {
-    // direct 7-point transform; the seventh roots come from the line's own twiddle table (7 | L)
-    cd w[7];
+// radix 7 (rare) is a direct 7-point transform written straight to its destination, one output per trip of a rolled loop so
+// that it does not set the register budget of the kernel; the seventh roots come from the line's global table (7 | L)
+__device__ __forceinline__ cd mr_dft7_out(const cd* v, int a, const cd* __restrict__ gtab, int L) {
+    cd s = v[0];
 #pragma unroll
-    for (int t = 0; t < 7; ++t) w[t] = __ldg(&tab[t * (L / 7)]);
-    cd o[7];
-#pragma unroll
-    for (int a = 0; a < 7; ++a) {
-        cd s = v[0];
-#pragma unroll
-        for (int b = 1; b < 7; ++b) s = cadd(s, cmul(v[b], w[(a * b) % 7]));
-        o[a] = s;
-    }
-#pragma unroll
-    for (int a = 0; a < 7; ++a) v[a] = o[a];
+    for (int b = 1; b < 7; ++b) s = cadd(s, cmul(v[b], __ldg(&gtab[((a * b) % 7) * (L / 7)])));
+    return s;
 }
 
 // shared-memory index of element e of line `line`: columns keep the lines of a tile interleaved (they arrive that way
 // from global memory), rows keep each line contiguous
-template <bool LINE_FAST> __device__ __forceinline__ int mr_idx(int e, int line, int TC, int L) {
-    return LINE_FAST ? e * TC + line : line * L + e;
+template <bool LINE_FAST> __device__ __forceinline__ int mr_idx(int e, int line, int lTC, int L) {
+    return LINE_FAST ? (e << lTC) + line : line * L + e;
 }
 
-template <int R, bool LINE_FAST>
-__device__ __forceinline__ void mr_stage(const MrSched& sc, const cd* __restrict__ src, cd* __restrict__ dst, const cd* __restrict__ tab, int Ns) {
-    const int L = sc.L, TC = sc.TC, nb = L / R, total = nb * TC;
+// one Stockham stage: butterfly j of a line reads elements j + m*L/R, multiplies by W_{Ns R}^(k m) (k = j mod Ns; one table
+// entry, the higher powers by multiplication: float64 pipe time is free here, table loads are not), transforms, and writes
+// (j - k) R + k + m Ns
+template <int R, bool LINE_FAST, int NT>
+__device__ __forceinline__ void mr_stage(const MrSched& sc, const cd* __restrict__ src, cd* __restrict__ dst, const cd* __restrict__ stab,
+                                         const cd* __restrict__ gtab, int Ns, uint32_t mNs, uint32_t mNb) {
+    const int L = sc.L, lTC = sc.lTC, nb = L / R, total = nb << lTC;
     const int twStep = L / (Ns * R);
-    for (int b = threadIdx.x; b < total; b += MR_THREADS) {
+#pragma unroll 1
+    for (int b = threadIdx.x; b < total; b += NT) {
         int line, j;
-        if (LINE_FAST) { line = b % TC; j = b / TC; } else { j = b % nb; line = b / nb; }
-        const int k = j % Ns;
+        if (LINE_FAST) { line = b & ((1 << lTC) - 1); j = b >> lTC; } else { line = nb > 1 ? mr_div(b, mNb) : b; j = b - line * nb; }
+        const int k = Ns > 1 ? j - mr_div(j, mNs) * Ns : 0;
         cd v[R];
 #pragma unroll
-        for (int m = 0; m < R; ++m) v[m] = src[mr_idx<LINE_FAST>(j + m * nb, line, TC, L)];
+        for (int m = 0; m < R; ++m) v[m] = src[mr_idx<LINE_FAST>(j + m * nb, line, lTC, L)];
         if (Ns > 1) {
+            const cd w1 = stab[k * twStep];
+            cd w = w1;
+            v[1] = cmul(v[1], w1);
 #pragma unroll
-            for (int m = 1; m < R; ++m) v[m] = cmul(v[m], __ldg(&tab[k * m * twStep]));
+            for (int m = 2; m < R; ++m) {
+                w = cmul(w, w1);
+                v[m] = cmul(v[m], w);
+            }
         }
-        mr_dft<R>(v, tab, L);
         const int j0 = (j - k) * R + k;
+        if constexpr (R == 7) {
+#pragma unroll 1
+            for (int m = 0; m < R; ++m) dst[mr_idx<LINE_FAST>(j0 + m * Ns, line, lTC, L)] = mr_dft7_out(v, m, gtab, L);
+        } else {
+            mr_dft<R>(v);
 #pragma unroll
-        for (int m = 0; m < R; ++m) dst[mr_idx<LINE_FAST>(j0 + m * Ns, line, TC, L)] = v[m];
+            for (int m = 0; m < R; ++m) dst[mr_idx<LINE_FAST>(j0 + m * Ns, line, lTC, L)] = v[m];
+        }
     }
 }
 
 // all stages of the tile held in `a`; returns the buffer that holds the (natural order) result
-template <bool LINE_FAST>
-__device__ __forceinline__ cd* mr_transform(const MrSched& sc, cd* a, cd* b, const cd* __restrict__ tab) {
+template <bool LINE_FAST, int NT>
+__device__ __forceinline__ cd* mr_transform(const MrSched& sc, cd* a, cd* b, const cd* __restrict__ stab, const cd* __restrict__ gtab) {
     int Ns = 1;
     for (int s = 0; s < sc.nStages; ++s) {
         const int R = sc.radix[s];
+        const uint32_t mNs = sc.mNs[s], mNb = sc.mNb[s];
         switch (R) {
-            case 2: mr_stage<2, LINE_FAST>(sc, a, b, tab, Ns); break;
-            case 3: mr_stage<3, LINE_FAST>(sc, a, b, tab, Ns); break;
-            case 4: mr_stage<4, LINE_FAST>(sc, a, b, tab, Ns); break;
-            case 5: mr_stage<5, LINE_FAST>(sc, a, b, tab, Ns); break;
-            default: mr_stage<7, LINE_FAST>(sc, a, b, tab, Ns); break;
+            case 2: mr_stage<2, LINE_FAST, NT>(sc, a, b, stab, gtab, Ns, mNs, mNb); break;
+            case 3: mr_stage<3, LINE_FAST, NT>(sc, a, b, stab, gtab, Ns, mNs, mNb); break;
+            case 4: mr_stage<4, LINE_FAST, NT>(sc, a, b, stab, gtab, Ns, mNs, mNb); break;
+            case 5: mr_stage<5, LINE_FAST, NT>(sc, a, b, stab, gtab, Ns, mNs, mNb); break;
+            default: mr_stage<7, LINE_FAST, NT>(sc, a, b, stab, gtab, Ns, mNs, mNb); break;
         }
         __syncthreads();
         cd* t = a; a = b; b = t;
@@ -144,17 +160,19 @@ __device__ __forceinline__ cd* mr_transform(const MrSched& sc, cd* a, cd* b, con
 struct MrColsParams {
     MrSched sc;                   // L = N1
     const void* samples; int64_t scanStride; const int64_t* offs; int nFrames;
-    const double* win; const cd* tabL; const cd* tabF; cd* Z;
+    const double* win; const cd* tabL; const cd* tabHi; const cd* tabLo; cd* Z;
     int64_t F; int N1, N2; int64_t nfs;
     double u8off, u8scale;
 };
 
-template <int INFMT>
-__global__ void __launch_bounds__(MR_THREADS, 2) mr_cols_kernel(const MrColsParams p) {
+template <int INFMT, int NT>
+__global__ void __launch_bounds__(NT, 2) mr_cols_kernel(const MrColsParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int TC = p.sc.TC, N1 = p.N1, N2 = p.N2;
+    const int TC = p.sc.TC, lTC = p.sc.lTC, N1 = p.N1, N2 = p.N2;
     cd* bufA = reinterpret_cast<cd*>(smem_raw);
     cd* bufB = bufA + (size_t)TC * N1;
+    cd* stab = bufB + (size_t)TC * N1;
+    for (int i = threadIdx.x; i < p.sc.tabN; i += NT) stab[i] = p.tabL[i];
     const int tpf = (N2 + TC - 1) / TC;                     // tiles per frame
     const int64_t tiles = p.nfs * tpf;
     const int items = TC * N1;
@@ -163,8 +181,9 @@ __global__ void __launch_bounds__(MR_THREADS, 2) mr_cols_kernel(const MrColsPara
         const int c0 = (int)(tile - fs * tpf) * TC;
         const int64_t s = fs / p.nFrames;
         const int64_t base = s * p.scanStride + __ldg(&p.offs[fs - s * p.nFrames]);
-        for (int i = threadIdx.x; i < items; i += MR_THREADS) {
-            const int line = i % TC, e = i / TC, n2 = c0 + line;
+#pragma unroll 4
+        for (int i = threadIdx.x; i < items; i += NT) {
+            const int line = i & (TC - 1), e = i >> lTC, n2 = c0 + line;
             cd v = make_double2(0.0, 0.0);
             if (n2 < N2) {
                 const int64_t n = (int64_t)e * N2 + n2;
@@ -173,10 +192,15 @@ __global__ void __launch_bounds__(MR_THREADS, 2) mr_cols_kernel(const MrColsPara
             bufA[i] = v;
         }
         __syncthreads();
-        const cd* res = mr_transform<true>(p.sc, bufA, bufB, p.tabL);
-        for (int i = threadIdx.x; i < items; i += MR_THREADS) {
-            const int line = i % TC, k1 = i / TC, n2 = c0 + line;
-            if (n2 < N2) p.Z[fs * p.F + (int64_t)k1 * N2 + n2] = cmul(res[i], __ldg(&p.tabF[(int64_t)n2 * k1]));
+        const cd* res = mr_transform<true, NT>(p.sc, bufA, bufB, stab, p.tabL);
+#pragma unroll 4
+        for (int i = threadIdx.x; i < items; i += NT) {
+            const int line = i & (TC - 1), k1 = i >> lTC, n2 = c0 + line;
+            if (n2 < N2) {
+                const int t = n2 * k1;                       // < F <= MR_MAX_LINE^2 < 2^31
+                const cd w = cmul(__ldg(&p.tabHi[t >> MR_TW_LO_BITS]), __ldg(&p.tabLo[t & ((1 << MR_TW_LO_BITS) - 1)]));
+                p.Z[fs * p.F + (int64_t)k1 * N2 + n2] = cmul(res[i], w);
+            }
         }
         __syncthreads();
     }
@@ -188,12 +212,14 @@ struct MrRowsParams {
     int64_t F; int N1, N2; int64_t nScans; int nFrames; int cumuMode;
 };
 
-template <int MR_MAXA>
-__global__ void __launch_bounds__(MR_THREADS, (MR_MAXA <= MR_MAXA_STD ? 2 : 1)) mr_rows_acc_kernel(const MrRowsParams p) {
+template <int MR_MAXA, int NT>
+__global__ void __launch_bounds__(NT, (MR_MAXA <= mr_maxa(MR_SMEM_STD, NT) ? 2 : 1)) mr_rows_acc_kernel(const MrRowsParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int TC = p.sc.TC, N1 = p.N1, N2 = p.N2;
     cd* bufA = reinterpret_cast<cd*>(smem_raw);
     cd* bufB = bufA + (size_t)TC * N2;
+    cd* stab = bufB + (size_t)TC * N2;
+    for (int i = threadIdx.x; i < p.sc.tabN; i += NT) stab[i] = p.tabL[i];
     const int tps = (N1 + TC - 1) / TC;                     // tiles per scan
     const int64_t tiles = p.nScans * tps;
     const int items = TC * N2;
@@ -203,15 +229,16 @@ __global__ void __launch_bounds__(MR_THREADS, (MR_MAXA <= MR_MAXA_STD ? 2 : 1)) 
         double acc[MR_MAXA];
         for (int f = 0; f < p.nFrames; ++f) {
             const cd* __restrict__ zf = p.Z + (s * p.nFrames + f) * p.F;
-            for (int i = threadIdx.x; i < items; i += MR_THREADS) {
-                const int line = i / N2, e = i - line * N2, k1 = r0 + line;
-                bufA[i] = (k1 < N1) ? zf[(int64_t)k1 * N2 + e] : make_double2(0.0, 0.0);
+#pragma unroll 4
+            for (int i = threadIdx.x; i < items; i += NT) {
+                const int line = mr_div(i, p.sc.mL), e = i - line * N2, k1 = r0 + line;
+                bufA[i] = (k1 < N1) ? __ldg(&zf[(int64_t)k1 * N2 + e]) : make_double2(0.0, 0.0);
             }
             __syncthreads();
-            const cd* res = mr_transform<false>(p.sc, bufA, bufB, p.tabL);
+            const cd* res = mr_transform<false, NT>(p.sc, bufA, bufB, stab, p.tabL);
 #pragma unroll
             for (int m = 0; m < MR_MAXA; ++m) {
-                const int i = threadIdx.x + MR_THREADS * m;
+                const int i = threadIdx.x + NT * m;
                 if (i < items) {
                     const cd x = res[i];
                     double mag = x.x * x.x + x.y * x.y;
@@ -227,42 +254,57 @@ __global__ void __launch_bounds__(MR_THREADS, (MR_MAXA <= MR_MAXA_STD ? 2 : 1)) 
         }
 #pragma unroll
         for (int m = 0; m < MR_MAXA; ++m) {
-            const int i = threadIdx.x + MR_THREADS * m;
+            const int i = threadIdx.x + NT * m;
             if (i < items) {
-                const int line = i / N2, k2 = i - line * N2, k1 = r0 + line;
+                const int line = mr_div(i, p.sc.mL), k2 = i - line * N2, k1 = r0 + line;
                 if (k1 < N1) p.acc[s * p.F + k1 + (int64_t)N1 * k2] = acc[m];
             }
         }
     }
 }
 
-__global__ void mr_table_kernel(cd* t, int64_t n) {
-    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+// t[k] = exp(-2 pi i k mult / n)
+__global__ void mr_table_kernel(cd* t, int64_t count, int64_t mult, int64_t n) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += (int64_t)gridDim.x * blockDim.x) {
         double s, c;
-        sincospi(-2.0 * (double)k / (double)n, &s, &c);
+        sincospi(-2.0 * (double)((k * mult) % n) / (double)n, &s, &c);
         t[k] = make_double2(c, s);
     }
 }
 
-// radix schedule of a line: odd radices first, then 4s, then a single 2
-bool mr_schedule(int L, int TC, MrSched* sc) {
-    sc->L = L; sc->TC = TC; sc->nStages = 0;
+uint32_t mr_magic(int d) { return (uint32_t)((((uint64_t)1 << 32) + (uint64_t)d - 1) / (uint64_t)d); }
+
+// radix schedule of a line: odd radices first (conflict-free strides), then 4s, then a single 2
+bool mr_schedule(int L, MrSched* sc) {
+    sc->L = L; sc->nStages = 0; sc->TC = 1; sc->lTC = 0;
     int rest = L;
     for (int r : {7, 5, 3}) while (rest % r == 0) { if (sc->nStages == MR_MAX_STAGES) return false; sc->radix[sc->nStages++] = r; rest /= r; }
     while (rest % 4 == 0) { if (sc->nStages == MR_MAX_STAGES) return false; sc->radix[sc->nStages++] = 4; rest /= 4; }
     if (rest % 2 == 0) { if (sc->nStages == MR_MAX_STAGES) return false; sc->radix[sc->nStages++] = 2; rest /= 2; }
-    return rest == 1;
+    if (rest != 1) return false;
+    sc->mL = mr_magic(L);
+    sc->tabN = 0;
+    int Ns = 1;
+    for (int s = 0; s < sc->nStages; ++s) {
+        sc->mNs[s] = mr_magic(Ns);
+        sc->mNb[s] = mr_magic(L / sc->radix[s]);
+        if (s > 0 && L / sc->radix[s] > sc->tabN) sc->tabN = L / sc->radix[s];
+        Ns *= sc->radix[s];
+    }
+    return true;
 }
 
-int mr_tile_lines(int L, int other) {
-    int budget = MR_TILE_TARGET;
-    if (const char* e = getenv("KSPEC_MR_TILE_ELEMS")) { const int v = atoi(e); if (v >= 1 && v <= MR_TILE_ELEMS) budget = v; }
-    int tc = budget / L;
+// lines per tile: the largest power of two whose buffer pair fits next to the twiddle table in `smem` bytes
+void mr_tile_lines(MrSched* sc, int other, int smem) {
+    int tc = (smem - sc->tabN * 16) / (32 * sc->L);
     if (tc > 32) tc = 32;
     if (tc > other) tc = other;
-    while (tc > 1 && (tc & (tc - 1))) --tc;           // power of two: whole sectors
-    return tc < 1 ? 1 : tc;
+    int l = 0;
+    while ((2 << l) <= tc) ++l;
+    sc->lTC = l;
+    sc->TC = 1 << l;
 }
+size_t mr_smem_bytes(const MrSched& sc) { return (size_t)2 * sc.TC * sc.L * 16 + (size_t)sc.tabN * 16; }
 
 }  // namespace
 
@@ -289,7 +331,7 @@ struct MixedRadix {
     double u8off = 0, u8scale = 0;
     cudaStream_t st = nullptr;
     double* dWin = nullptr;
-    cd *dTab1 = nullptr, *dTab2 = nullptr, *dTabF = nullptr, *dZ = nullptr;
+    cd *dTab1 = nullptr, *dTab2 = nullptr, *dTabHi = nullptr, *dTabLo = nullptr, *dZ = nullptr;
     int64_t* dOffs = nullptr;
     int nOffs = 0;
     size_t zCap = 0;
@@ -297,7 +339,7 @@ struct MixedRadix {
 
 void mixedradix_destroy(MixedRadix* b) {
     if (!b) return;
-    for (void* p : {(void*)b->dWin, (void*)b->dTab1, (void*)b->dTab2, (void*)b->dTabF, (void*)b->dZ, (void*)b->dOffs})
+    for (void* p : {(void*)b->dWin, (void*)b->dTab1, (void*)b->dTab2, (void*)b->dTabHi, (void*)b->dTabLo, (void*)b->dZ, (void*)b->dOffs})
         if (p) cudaFree(p);
     delete b;
 }
@@ -323,8 +365,7 @@ MixedRadix* mixedradix_create(int prec, int inFmt, int64_t F, const double* wind
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&b->smCount, cudaDevAttrMultiProcessorCount, dev);
-    if (!mixedradix_split(F, &b->N1, &b->N2) || !mr_schedule(b->N1, mr_tile_lines(b->N1, b->N2), &b->sc1) ||
-        !mr_schedule(b->N2, mr_tile_lines(b->N2, b->N1), &b->sc2)) {
+    if (!mixedradix_split(F, &b->N1, &b->N2) || !mr_schedule(b->N1, &b->sc1) || !mr_schedule(b->N2, &b->sc2)) {
         snprintf(err, errLen, "fftSize %lld has no mixed-radix split", (long long)F);
         mixedradix_destroy(b);
         return nullptr;
@@ -333,10 +374,19 @@ MixedRadix* mixedradix_create(int prec, int inFmt, int64_t F, const double* wind
     MCK(cudaMemcpyAsync(b->dWin, window, (size_t)F * 8, cudaMemcpyHostToDevice, st));
     MCK(cudaMalloc(&b->dTab1, (size_t)b->N1 * 16));
     MCK(cudaMalloc(&b->dTab2, (size_t)b->N2 * 16));
-    MCK(cudaMalloc(&b->dTabF, (size_t)F * 16));
-    mr_table_kernel<<<64, 256, 0, st>>>(b->dTab1, b->N1);
-    mr_table_kernel<<<64, 256, 0, st>>>(b->dTab2, b->N2);
-    mr_table_kernel<<<1024, 256, 0, st>>>(b->dTabF, F);
+    int smem = MR_SMEM_STD;
+    if (const char* e = getenv("KSPEC_MR_SMEM")) { const int v = atoi(e); if (v >= 16 * 1024 && v <= MR_SMEM_BIG) smem = v; }
+    for (MrSched* sc : {&b->sc1, &b->sc2}) {
+        mr_tile_lines(sc, sc == &b->sc1 ? b->N2 : b->N1, smem);
+        if (mr_smem_bytes(*sc) > (size_t)smem) mr_tile_lines(sc, 1, MR_SMEM_BIG);       // a long line: one per CTA, one CTA per SM
+    }
+    const int64_t nHi = (F >> MR_TW_LO_BITS) + 1, nLo = (int64_t)1 << MR_TW_LO_BITS;
+    MCK(cudaMalloc(&b->dTabHi, (size_t)nHi * 16));
+    MCK(cudaMalloc(&b->dTabLo, (size_t)nLo * 16));
+    mr_table_kernel<<<64, 256, 0, st>>>(b->dTab1, b->N1, 1, b->N1);
+    mr_table_kernel<<<64, 256, 0, st>>>(b->dTab2, b->N2, 1, b->N2);
+    mr_table_kernel<<<64, 256, 0, st>>>(b->dTabHi, nHi, nLo, F);
+    mr_table_kernel<<<64, 256, 0, st>>>(b->dTabLo, nLo, 1, F);
     MCK(cudaGetLastError());
     MCK(cudaStreamSynchronize(st));
     return b;
@@ -371,17 +421,27 @@ int mixedradix_run(MixedRadix* b, const void* samples, int64_t scanStride, int64
         b->zCap = need;
     }
     const size_t eb = b->inFmt == KSPEC_IN_U8_IQ ? 2 : (b->inFmt == KSPEC_IN_C64 ? 8 : 16);
-    const size_t smem1 = (size_t)2 * b->sc1.TC * b->N1 * 16, smem2 = (size_t)2 * b->sc2.TC * b->N2 * 16;
-    auto kr = (b->sc2.TC * b->N2 <= MR_MAXA_STD * MR_THREADS) ? mr_rows_acc_kernel<MR_MAXA_STD> : mr_rows_acc_kernel<MR_MAXA_BIG>;
-    auto kc = b->inFmt == KSPEC_IN_U8_IQ ? mr_cols_kernel<KSPEC_IN_U8_IQ> : (b->inFmt == KSPEC_IN_C64 ? mr_cols_kernel<KSPEC_IN_C64> : mr_cols_kernel<KSPEC_IN_C128>);
+    const size_t smem1 = mr_smem_bytes(b->sc1), smem2 = mr_smem_bytes(b->sc2);
+    int nt = MR_THREADS;
+    if (const char* e = getenv("KSPEC_MR_THREADS")) { if (atoi(e) == 256) nt = 256; }
+    void (*kr)(const MrRowsParams);
+    void (*kc)(const MrColsParams);
+    const bool stdTile = smem2 <= (size_t)MR_SMEM_STD;
+    if (nt == 512) {
+        kr = stdTile ? mr_rows_acc_kernel<mr_maxa(MR_SMEM_STD, 512), 512> : mr_rows_acc_kernel<mr_maxa(MR_SMEM_BIG, 512), 512>;
+        kc = b->inFmt == KSPEC_IN_U8_IQ ? mr_cols_kernel<KSPEC_IN_U8_IQ, 512> : (b->inFmt == KSPEC_IN_C64 ? mr_cols_kernel<KSPEC_IN_C64, 512> : mr_cols_kernel<KSPEC_IN_C128, 512>);
+    } else {
+        kr = stdTile ? mr_rows_acc_kernel<mr_maxa(MR_SMEM_STD, 256), 256> : mr_rows_acc_kernel<mr_maxa(MR_SMEM_BIG, 256), 256>;
+        kc = b->inFmt == KSPEC_IN_U8_IQ ? mr_cols_kernel<KSPEC_IN_U8_IQ, 256> : (b->inFmt == KSPEC_IN_C64 ? mr_cols_kernel<KSPEC_IN_C64, 256> : mr_cols_kernel<KSPEC_IN_C128, 256>);
+    }
     if (cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1) != cudaSuccess ||
         cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2) != cudaSuccess) {
         set_error("mixed-radix shared memory request failed: %s", cudaGetErrorString(cudaGetLastError()));
         return KSPEC_ERR_CUDA;
     }
     int per1 = 1, per2 = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per1, kc, MR_THREADS, smem1);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per2, kr, MR_THREADS, smem2);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per1, kc, nt, smem1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per2, kr, nt, smem2);
     if (per1 < 1) per1 = 1;
     if (per2 < 1) per2 = 1;
     double* dAcc = reinterpret_cast<double*>(acc);
@@ -389,14 +449,14 @@ int mixedradix_run(MixedRadix* b, const void* samples, int64_t scanStride, int64
         const int64_t ns = (nScans - s0 < chunk) ? nScans - s0 : chunk;
         const int64_t nfs = ns * nFrames;
         const void* smp = reinterpret_cast<const unsigned char*>(samples) + (size_t)s0 * scanStride * eb;
-        MrColsParams pc{b->sc1, smp, scanStride, b->dOffs, nFrames, b->dWin, b->dTab1, b->dTabF, b->dZ, b->F, b->N1, b->N2, nfs, b->u8off, b->u8scale};
+        MrColsParams pc{b->sc1, smp, scanStride, b->dOffs, nFrames, b->dWin, b->dTab1, b->dTabHi, b->dTabLo, b->dZ, b->F, b->N1, b->N2, nfs, b->u8off, b->u8scale};
         const int64_t t1 = nfs * ((b->N2 + b->sc1.TC - 1) / b->sc1.TC);
         const int64_t cap1 = (int64_t)b->smCount * per1;
-        kc<<<(int)(t1 < cap1 ? t1 : cap1), MR_THREADS, smem1, st>>>(pc);
+        kc<<<(int)(t1 < cap1 ? t1 : cap1), nt, smem1, st>>>(pc);
         MrRowsParams pr{b->sc2, b->dZ, b->dTab2, dAcc + s0 * b->F, b->F, b->N1, b->N2, ns, nFrames, cumuMode};
         const int64_t t2 = ns * ((b->N1 + b->sc2.TC - 1) / b->sc2.TC);
         const int64_t cap2 = (int64_t)b->smCount * per2;
-        kr<<<(int)(t2 < cap2 ? t2 : cap2), MR_THREADS, smem2, st>>>(pr);
+        kr<<<(int)(t2 < cap2 ? t2 : cap2), nt, smem2, st>>>(pr);
         *launches += 2;
     }
     const cudaError_t e = cudaGetLastError();

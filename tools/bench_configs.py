@@ -29,12 +29,30 @@ CONFIGS = [
     ("cfg5a scan 4096 ones r=0.1 f64", 4096, "ones", 0.1, "AVG", "f64", 1024, "c64"),
     ("reference default 16384 ones r=0.1 f32", 16384, "ones", 0.1, "AVG", "f32", 512, "c64"),
     ("cfg4 2^21 ones MAX r=0.1 (four-step) f64", 1 << 21, "ones", 0.1, "MAX", "f64", 4, "c64"),
-    ("cfg5b 2400000 ones r=0.1 (Bluestein 2^23) f64", 2400000, "ones", 0.1, "AVG", "f64", 2, "c64"),
+    ("cfg5b 2400000 ones r=0.1 (mixed radix 1500x1600) f64", 2400000, "ones", 0.1, "AVG", "f64", 4, "c64"),
+    ("cfg5b 2400000 ones r=0.1 (Bluestein 2^23, forced) f64", 2400000, "ones", 0.1, "AVG", "f64", 2, "c64", {"KSPEC_FORCE_BLUESTEIN": "1"}),
+    ("48000 hanning r=0.5 (mixed radix 200x240) f64", 48000, "hanning", 0.5, "AVG", "f64", 256, "c64"),
+    ("48000 hanning r=0.5 (Bluestein 2^17, forced) f64", 48000, "hanning", 0.5, "AVG", "f64", 256, "c64", {"KSPEC_FORCE_BLUESTEIN": "1"}),
 ]
 
 
 def main():
-    for name, F, win, r, cumu, prec, n_scans, ingest in CONFIGS:
+    only = os.environ.get("KSPEC_CFG_FILTER", "")
+    for cfg in CONFIGS:
+        name, F, win, r, cumu, prec, n_scans, ingest = cfg[:8]
+        if only and only not in name:
+            continue
+        env = cfg[8] if len(cfg) > 8 else {}
+        os.environ.update(env)
+        try:
+            run_one(name, F, win, r, cumu, prec, n_scans, ingest)
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+
+
+def run_one(name, F, win, r, cumu, prec, n_scans, ingest):
+    if True:
         d = derive_config(dict(fftSize=F, window=win, samplingRate=FS))
         S = d["fullSize"]
         fmt = _ffi.IN_U8_IQ if ingest == "u8" else _ffi.IN_C64
