@@ -27,8 +27,20 @@ int KSPEC_INST_NAME(int log2F, int variant, const ScanParams& p, int grid, cudaS
         }
     }
     if (variant != SMEM_VARIANT_BASE) return (int)cudaErrorInvalidValue;
+    if constexpr (!F32) {
+        // fftSize 2048 in float64 (the default precision): one exchange buffer and one TMA stage leave room for three CTAs per
+        // SM instead of two: 81 -> 96 G samples/s (profiles/README.md)
+        if (log2F == 11) {
+#ifdef KSPEC_INST_VARIANTS
+            static const int forced = [] { const char* e = getenv("KSPEC_VARIANT64"); return e ? atoi(e) : -1; }();
+            if (forced == 0) return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, 11, 0>(p, grid, st, info);
+            if (forced == 9) return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, 11, 9>(p, grid, st, info);
+#endif
+            return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, 11, 8>(p, grid, st, info);
+        }
+    }
     switch (log2F) {
-#define KSPEC_CASE(L) case L: if constexpr (L <= KSPEC_INST_MAXLOG2F && !(F32 && L == 11)) return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, L>(p, grid, st, info); else break;
+#define KSPEC_CASE(L) case L: if constexpr (L <= KSPEC_INST_MAXLOG2F && L != 11) return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, L>(p, grid, st, info); else break;
         KSPEC_CASE(4) KSPEC_CASE(5) KSPEC_CASE(6) KSPEC_CASE(7) KSPEC_CASE(8) KSPEC_CASE(9) KSPEC_CASE(10)
         KSPEC_CASE(11) KSPEC_CASE(12) KSPEC_CASE(13) KSPEC_CASE(14)
 #undef KSPEC_CASE
