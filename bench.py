@@ -257,12 +257,15 @@ def run_ours(args):
     for i in range(N_SCANS // BASE_SCANS):
         plan.dev_upload(d_samples, base, offset=i * base.nbytes)
     # pinned host copy for the end-to-end leg
-    host = None
+    host = host_out = None
     if not os.environ.get("KSPEC_BENCH_FAST"):
         pinned = _ffi.PinnedBuffer(N_SCANS * S * 8)
         host = pinned.view(np.complex64)
         for i in range(N_SCANS // BASE_SCANS):
             host[i * len(base):(i + 1) * len(base)] = base
+        # the waterfall rows come back into a pinned buffer the caller owns and reuses (64 MiB per step)
+        pinned_out = _ffi.PinnedBuffer(N_SCANS * XRES * 8)
+        host_out = {"hm_rows": pinned_out.view(np.float64).reshape(N_SCANS, XRES)}
 
     comm = None
     if world > 1:
@@ -287,7 +290,7 @@ def run_ours(args):
 
     def step_e2e():
         out = plan.zerospan_batch(host, N_SCANS, GAIN, XRES, "MAX", rows=None, want_hm=True,
-                                  scan_index_base=base_idx, n_scans_total=total_scans)
+                                  scan_index_base=base_idx, n_scans_total=total_scans, out=host_out)
         if comm is not None:
             comm.allreduce_host(out["max"], out["min"], out["avg"])
         return out

@@ -62,6 +62,8 @@ struct kspec_plan {
     double u8off = 0, u8scale = 0, winAdj = 0, linScale = 0;
     std::vector<int64_t> offs;
     cudaStream_t st = nullptr;
+    cudaStream_t stCopy = nullptr;                 // host->device chunks of a pipelined host batch
+    std::vector<cudaEvent_t> evChunk;              // "chunk k has arrived"
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int smCount = 0;
     int smReserve = 0;
@@ -396,6 +398,8 @@ int kspec_plan_destroy(kspec_plan* pl) {
     for (int i = 0; i < kspec_plan::KT; ++i) { if (pl->kev[i][0]) cudaEventDestroy(pl->kev[i][0]); if (pl->kev[i][1]) cudaEventDestroy(pl->kev[i][1]); }
     if (pl->ev0) cudaEventDestroy(pl->ev0);
     if (pl->ev1) cudaEventDestroy(pl->ev1);
+    for (cudaEvent_t e : pl->evChunk) cudaEventDestroy(e);
+    if (pl->stCopy) cudaStreamDestroy(pl->stCopy);
     if (pl->st) cudaStreamDestroy(pl->st);
     delete pl;
     return KSPEC_OK;
@@ -420,56 +424,90 @@ int kspec_plan_info(const kspec_plan* pl, kspec_plan_info_t* info) {
 }
 
 // ---- device-resident batch ---------------------------------------------------------------------------------------
-int kspec_zerospan_batch_dev(kspec_plan* pl, const void* dSamples, int64_t nScans, double gain, const double* adj, int hmMode,
-                             int xRes, int rowsKind, int wantHm, const double* mx, const double* mn, const double* av, int carry,
-                             int64_t scanIndexBase, int64_t nScansTotal) {
-    if (check_plan(pl)) return KSPEC_ERR_ARG;
-    if (!dSamples || nScans < 1) { set_error("no scans"); return KSPEC_ERR_ARG; }
-    if (rowsKind < KSPEC_ROWS_NONE || rowsKind > KSPEC_ROWS_DB) { set_error("unknown rowsKind %d", rowsKind); return KSPEC_ERR_ARG; }
-    if (hmMode < KSPEC_COMPRESS_RAW || hmMode > KSPEC_COMPRESS_MIN) { set_error("unknown pltCompressHM %d", hmMode); return KSPEC_ERR_ARG; }
-    if (carry && (!mx || !mn || !av)) { set_error("carry requested without max/min/avg state"); return KSPEC_ERR_ARG; }
-    if (nScansTotal < scanIndexBase + nScans || scanIndexBase < 0) { set_error("shard [%lld,+%lld) outside capture of %lld scans", (long long)scanIndexBase, (long long)nScans, (long long)nScansTotal); return KSPEC_ERR_ARG; }
+namespace {
+
+// One engine launch + stats for scans [scanOfs, scanOfs + nScans) of a batch whose samples start at dSamples (already
+// offset) and whose row buffers (pl->rows / pl->hm, reserved by the caller for the whole batch) receive this part at row
+// scanOfs.  dCarry: device [max|min|avg] to continue from, or nullptr.  Leaves [max|min|avg] in pl->stats.
+int zerospan_part(kspec_plan* pl, const void* dSamples, int64_t nScans, int64_t scanOfs, double gain, bool haveAdj, int hmMode, int W,
+                  int rowsKind, bool wantHm, const double* dCarry, int firstIsSeed, double avgScale) {
     const int F = pl->F;
-    const int W = hm_width(F, xRes, hmMode);
-    if (wantHm && (xRes < 1 || F % W != 0)) { set_error("fftSize %d is not a multiple of the waterfall width %d (xRes must divide fftSize, K:941-949)", F, W); return KSPEC_ERR_ARG; }
-    DeviceGuard guard(pl->device);
     const size_t rb = real_bytes(pl->prec);
     int rc;
     ScanParams p = base_params(pl, dSamples, nScans);
     p.gain = gain;
     p.rowsKind = rowsKind;
-    if (rowsKind != KSPEC_ROWS_NONE) { if ((rc = pl->rows.reserve((size_t)nScans * F * rb))) return rc; p.rows = pl->rows.p; }
-    if (wantHm) { if ((rc = pl->hm.reserve((size_t)nScans * W * rb))) return rc; p.hm = pl->hm.p; p.hmMode = hmMode; p.hmW = W; }
+    if (rowsKind != KSPEC_ROWS_NONE) p.rows = (char*)pl->rows.p + (size_t)scanOfs * F * rb;
+    if (wantHm) { p.hm = (char*)pl->hm.p + (size_t)scanOfs * W * rb; p.hmMode = hmMode; p.hmW = W; }
     p.wantStats = 1;
     p.avgWin = (int)(nScans < AVG_WINDOW ? nScans : AVG_WINDOW);
     if ((rc = pl->avgRows.reserve((size_t)p.avgWin * F * rb))) return rc;
     p.avgRows = pl->avgRows.p;
+    if (haveAdj) p.adj = pl->adj.p;
+    int slots = 0;
+    if ((rc = run_engine(pl, p, &slots))) return rc;
+    launch_stats_finish(pl->prec, pl->wsMax.p, pl->wsMin.p, slots, pl->avgRows.p, p.avgWin, F, dCarry, firstIsSeed, avgScale,
+                        (double*)pl->stats.p, pl->st);
+    pl->launches += 1;
+    CK(cudaGetLastError());
+    return KSPEC_OK;
+}
+
+int zerospan_check(kspec_plan* pl, const void* samples, int64_t nScans, int hmMode, int xRes, int rowsKind, int wantHm, const double* mx,
+                   const double* mn, const double* av, int carry, int64_t scanIndexBase, int64_t nScansTotal, int* W) {
+    if (check_plan(pl)) return KSPEC_ERR_ARG;
+    if (!samples || nScans < 1) { set_error("no scans"); return KSPEC_ERR_ARG; }
+    if (rowsKind < KSPEC_ROWS_NONE || rowsKind > KSPEC_ROWS_DB) { set_error("unknown rowsKind %d", rowsKind); return KSPEC_ERR_ARG; }
+    if (hmMode < KSPEC_COMPRESS_RAW || hmMode > KSPEC_COMPRESS_MIN) { set_error("unknown pltCompressHM %d", hmMode); return KSPEC_ERR_ARG; }
+    if (carry && (!mx || !mn || !av)) { set_error("carry requested without max/min/avg state"); return KSPEC_ERR_ARG; }
+    if (nScansTotal < scanIndexBase + nScans || scanIndexBase < 0) { set_error("shard [%lld,+%lld) outside capture of %lld scans", (long long)scanIndexBase, (long long)nScans, (long long)nScansTotal); return KSPEC_ERR_ARG; }
+    *W = hm_width(pl->F, xRes, hmMode);
+    if (wantHm && (xRes < 1 || pl->F % *W != 0)) { set_error("fftSize %d is not a multiple of the waterfall width %d (xRes must divide fftSize, K:941-949)", pl->F, *W); return KSPEC_ERR_ARG; }
+    return KSPEC_OK;
+}
+
+// buffers and uploads shared by every part of a batch: row buffers, adj, host carry -> pl->carry
+int zerospan_prepare(kspec_plan* pl, int64_t nScans, int W, int rowsKind, bool wantHm, const double* adj, const double* mx, const double* mn,
+                     const double* av, int carry) {
+    const int F = pl->F;
+    const size_t rb = real_bytes(pl->prec);
+    int rc;
+    if (rowsKind != KSPEC_ROWS_NONE && (rc = pl->rows.reserve((size_t)nScans * F * rb))) return rc;
+    if (wantHm && (rc = pl->hm.reserve((size_t)nScans * W * rb))) return rc;
     if (adj) {
         if ((rc = pl->adj64.reserve((size_t)F * 8)) || (rc = pl->adj.reserve((size_t)F * rb))) return rc;
         CK(cudaMemcpyAsync(pl->adj64.p, adj, (size_t)F * 8, cudaMemcpyHostToDevice, pl->st));
         launch_narrow(pl->prec, (const double*)pl->adj64.p, pl->adj.p, F, pl->st);
         pl->launches += 1;
-        p.adj = pl->adj.p;
     }
-    if ((rc = pl->stats.reserve((size_t)3 * F * 8))) return rc;
-    const double* dCarry = nullptr;
+    if ((rc = pl->stats.reserve((size_t)3 * F * 8)) || (rc = pl->carry.reserve((size_t)3 * F * 8))) return rc;
     if (carry) {
-        if ((rc = pl->carry.reserve((size_t)3 * F * 8))) return rc;
         CK(cudaMemcpyAsync(pl->carry.p, mx, (size_t)F * 8, cudaMemcpyHostToDevice, pl->st));
         CK(cudaMemcpyAsync((double*)pl->carry.p + F, mn, (size_t)F * 8, cudaMemcpyHostToDevice, pl->st));
         CK(cudaMemcpyAsync((double*)pl->carry.p + 2 * F, av, (size_t)F * 8, cudaMemcpyHostToDevice, pl->st));
-        dCarry = (const double*)pl->carry.p;
     }
-    int slots = 0;
-    if ((rc = run_engine(pl, p, &slots))) return rc;
-    // Avg: this shard's part of the halving recurrence, pre-weighted for a SUM over shards
+    return KSPEC_OK;
+}
+
+// weight of this shard's Avg partial so that a SUM over shards equals the sequential halving recurrence
+double shard_avg_scale(int64_t scanIndexBase, int64_t nScans, int64_t nScansTotal) {
     const int64_t after = nScansTotal - (scanIndexBase + nScans);
-    const double avgScale = after == 0 ? 1.0 : ldexp(1.0, (int)(after > 2000 ? -2000 : -after));
-    const int firstIsSeed = (!carry && scanIndexBase == 0) ? 1 : 0;
-    launch_stats_finish(pl->prec, pl->wsMax.p, pl->wsMin.p, slots, pl->avgRows.p, p.avgWin, F, dCarry, firstIsSeed, avgScale,
-                        (double*)pl->stats.p, pl->st);
-    pl->launches += 1;
-    CK(cudaGetLastError());
+    return after == 0 ? 1.0 : ldexp(1.0, (int)(after > 2000 ? -2000 : -after));
+}
+
+}  // namespace
+
+int kspec_zerospan_batch_dev(kspec_plan* pl, const void* dSamples, int64_t nScans, double gain, const double* adj, int hmMode,
+                             int xRes, int rowsKind, int wantHm, const double* mx, const double* mn, const double* av, int carry,
+                             int64_t scanIndexBase, int64_t nScansTotal) {
+    int W = 0, rc;
+    if ((rc = zerospan_check(pl, dSamples, nScans, hmMode, xRes, rowsKind, wantHm, mx, mn, av, carry, scanIndexBase, nScansTotal, &W))) return rc;
+    DeviceGuard guard(pl->device);
+    if ((rc = zerospan_prepare(pl, nScans, W, rowsKind, wantHm != 0, adj, mx, mn, av, carry))) return rc;
+    if ((rc = zerospan_part(pl, dSamples, nScans, 0, gain, adj != nullptr, hmMode, W, rowsKind, wantHm != 0,
+                            carry ? (const double*)pl->carry.p : nullptr, (!carry && scanIndexBase == 0) ? 1 : 0,
+                            shard_avg_scale(scanIndexBase, nScans, nScansTotal))))
+        return rc;
     pl->lastScans = nScans; pl->lastRowsKind = rowsKind; pl->lastW = W; pl->lastHm = wantHm != 0; pl->haveBatch = true;
     return KSPEC_OK;
 }
@@ -566,14 +604,80 @@ int kspec_zerospan_batch(kspec_plan* pl, const void* samples, int64_t nScans, do
     if (!samples || nScans < 1) { set_error("no scans"); return KSPEC_ERR_ARG; }
     if (rows == nullptr) rowsKind = KSPEC_ROWS_NONE;
     DeviceGuard guard(pl->device);
-    const size_t bytes = (size_t)nScans * pl->S * in_elem_bytes(pl->inFmt);
+    const size_t scanBytes = (size_t)pl->S * in_elem_bytes(pl->inFmt);
+    const size_t bytes = (size_t)nScans * scanBytes;
     int rc;
     if ((rc = pl->in.reserve(bytes + TAIL_PAD))) return rc;
-    CK(cudaMemcpyAsync(pl->in.p, samples, bytes, cudaMemcpyHostToDevice, pl->st));
-    if ((rc = kspec_zerospan_batch_dev(pl, pl->in.p, nScans, gain, adj, hmMode, xRes, rowsKind, hm_rows != nullptr, mx, mn, av, carry,
-                                       scanIndexBase, nScansTotal)))
-        return rc;
-    return kspec_zerospan_fetch(pl, rows, hm_rows, mx, mn, av);
+    // Large host batches are pipelined: the samples cross PCIe in chunks on a copy stream while the engine works on the
+    // chunks that have arrived (each chunk continues from the previous one's Max/Min/Avg, like consecutive batches with
+    // carry) and the finished rows flow back; the exposed time is one chunk's copy plus one chunk's compute.
+    size_t chunkBytes = (size_t)256 << 20;
+    if (const char* e = getenv("KSPEC_PIPELINE_CHUNK_BYTES")) { const long long v = atoll(e); if (v > 0) chunkBytes = (size_t)v; }
+    int64_t chunkScans = (int64_t)(chunkBytes / scanBytes);
+    if (chunkScans < AVG_WINDOW) chunkScans = AVG_WINDOW;        // every part must hold the whole Avg window of its own rows
+    if (nScans < 2 * chunkScans) {
+        CK(cudaMemcpyAsync(pl->in.p, samples, bytes, cudaMemcpyHostToDevice, pl->st));
+        if ((rc = kspec_zerospan_batch_dev(pl, pl->in.p, nScans, gain, adj, hmMode, xRes, rowsKind, hm_rows != nullptr, mx, mn, av, carry,
+                                           scanIndexBase, nScansTotal)))
+            return rc;
+        return kspec_zerospan_fetch(pl, rows, hm_rows, mx, mn, av);
+    }
+    int W = 0;
+    const bool wantHm = hm_rows != nullptr;
+    if ((rc = zerospan_check(pl, samples, nScans, hmMode, xRes, rowsKind, wantHm, mx, mn, av, carry, scanIndexBase, nScansTotal, &W))) return rc;
+    const int F = pl->F;
+    const size_t rb = real_bytes(pl->prec);
+    const int64_t nChunks = (nScans + chunkScans - 1) / chunkScans;
+    if (!pl->stCopy) CK(cudaStreamCreateWithFlags(&pl->stCopy, cudaStreamNonBlocking));
+    while ((int64_t)pl->evChunk.size() < nChunks + 1) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        pl->evChunk.push_back(e);
+    }
+    if ((rc = zerospan_prepare(pl, nScans, W, rowsKind, wantHm, adj, mx, mn, av, carry))) return rc;
+    const bool f32 = pl->prec == KSPEC_PREC_F32;
+    const size_t rowElems = rowsKind != KSPEC_ROWS_NONE ? (size_t)nScans * F : 0, hmElems = wantHm ? (size_t)nScans * W : 0;
+    if (f32 && (rc = pl->wide.reserve((rowElems + hmElems) * 8))) return rc;
+    // the copy stream may not overwrite samples an earlier batch is still reading
+    CK(cudaEventRecord(pl->evChunk[nChunks], pl->st));
+    CK(cudaStreamWaitEvent(pl->stCopy, pl->evChunk[nChunks], 0));
+    for (int64_t c = 0; c < nChunks; ++c) {
+        const int64_t s0 = c * chunkScans, ns = (nScans - s0 < chunkScans) ? nScans - s0 : chunkScans;
+        CK(cudaMemcpyAsync((char*)pl->in.p + (size_t)s0 * scanBytes, (const char*)samples + (size_t)s0 * scanBytes, (size_t)ns * scanBytes,
+                           cudaMemcpyHostToDevice, pl->stCopy));
+        CK(cudaEventRecord(pl->evChunk[c], pl->stCopy));
+    }
+    for (int64_t c = 0; c < nChunks; ++c) {
+        const int64_t s0 = c * chunkScans, ns = (nScans - s0 < chunkScans) ? nScans - s0 : chunkScans;
+        const bool last = c == nChunks - 1;
+        CK(cudaStreamWaitEvent(pl->st, pl->evChunk[c], 0));
+        const bool cont = carry || c > 0;
+        if (c > 0) CK(cudaMemcpyAsync(pl->carry.p, pl->stats.p, (size_t)3 * F * 8, cudaMemcpyDeviceToDevice, pl->st));
+        if ((rc = zerospan_part(pl, (const char*)pl->in.p + (size_t)s0 * scanBytes, ns, s0, gain, adj != nullptr, hmMode, W, rowsKind, wantHm,
+                                cont ? (const double*)pl->carry.p : nullptr, (!cont && scanIndexBase == 0) ? 1 : 0,
+                                last ? shard_avg_scale(scanIndexBase, nScans, nScansTotal) : 1.0)))
+            return rc;
+        // rows of this chunk back to the caller
+        if (rowsKind != KSPEC_ROWS_NONE) {
+            const size_t o = (size_t)s0 * F, n = (size_t)ns * F;
+            const void* src = (const char*)pl->rows.p + o * rb;
+            if (f32) { launch_widen(pl->prec, src, (double*)pl->wide.p + o, (int64_t)n, pl->st); pl->launches += 1; src = (double*)pl->wide.p + o; }
+            CK(cudaMemcpyAsync(rows + o, src, n * 8, cudaMemcpyDeviceToHost, pl->st));
+        }
+        if (wantHm) {
+            const size_t o = (size_t)s0 * W, n = (size_t)ns * W;
+            const void* src = (const char*)pl->hm.p + o * rb;
+            if (f32) { launch_widen(pl->prec, src, (double*)pl->wide.p + rowElems + o, (int64_t)n, pl->st); pl->launches += 1; src = (double*)pl->wide.p + rowElems + o; }
+            CK(cudaMemcpyAsync(hm_rows + o, src, n * 8, cudaMemcpyDeviceToHost, pl->st));
+        }
+    }
+    pl->lastScans = nScans; pl->lastRowsKind = rowsKind; pl->lastW = W; pl->lastHm = wantHm; pl->haveBatch = true;
+    const double* st3 = (const double*)pl->stats.p;
+    if (mx) CK(cudaMemcpyAsync(mx, st3, (size_t)F * 8, cudaMemcpyDeviceToHost, pl->st));
+    if (mn) CK(cudaMemcpyAsync(mn, st3 + F, (size_t)F * 8, cudaMemcpyDeviceToHost, pl->st));
+    if (av) CK(cudaMemcpyAsync(av, st3 + 2 * F, (size_t)F * 8, cudaMemcpyDeviceToHost, pl->st));
+    CK(cudaStreamSynchronize(pl->st));
+    return KSPEC_OK;
 }
 
 int kspec_curscan(kspec_plan* pl, const void* samples, double* out) {

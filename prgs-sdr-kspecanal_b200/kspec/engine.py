@@ -90,15 +90,28 @@ class Plan:
 
     # -- zero_span loop body (K:464-484) over n scans ---------------------------------------------------
     def zerospan_batch(self, samples, n_scans, gain, x_res, hm_mode="MAX", adj=None, rows=None, want_hm=True,
-                       state=None, scan_index_base=0, n_scans_total=None):
+                       state=None, scan_index_base=0, n_scans_total=None, out=None):
         """rows: None | "linear" | "db".  state: (max, min, avg) float64 arrays carried in, or None.
+        out: optional dict(rows=, hm_rows=) of caller-owned float64 arrays to receive the rows (views of a
+        ``_ffi.PinnedBuffer`` make the device-to-host copies run at the PCIe rate instead of through pageable staging).
         Returns dict(rows, hm_rows, max, min, avg)."""
         a = self._samples(samples, n_scans)
         F = self.fft_size
         kind = {None: _ffi.ROWS_NONE, "linear": _ffi.ROWS_LINEAR, "db": _ffi.ROWS_DB}[rows]
-        rows_out = np.empty((n_scans, F), dtype=np.float64) if kind else None
         W = heatmap_width(F, x_res, hm_mode)
-        hm_out = np.empty((n_scans, W), dtype=np.float64) if want_hm else None
+
+        def _out(key, shape, wanted):
+            if not wanted:
+                return None
+            buf = None if out is None else out.get(key)
+            if buf is None:
+                return np.empty(shape, dtype=np.float64)
+            if buf.dtype != np.float64 or not buf.flags["C_CONTIGUOUS"] or buf.shape != shape:
+                raise ValueError("out[%s] must be a contiguous float64 array of shape %s" % (key, shape))
+            return buf
+
+        rows_out = _out("rows", (n_scans, F), bool(kind))
+        hm_out = _out("hm_rows", (n_scans, W), want_hm)
         if state is not None:
             mx, mn, av = (np.array(s, dtype=np.float64, copy=True) for s in state)
         else:

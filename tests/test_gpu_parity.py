@@ -680,3 +680,36 @@ def test_use_psd_needs_float64():
     from kspec.engine import KspecError
     with pytest.raises(KspecError):
         Plan(2048, 16384, 0.5, np.hanning(2048), "PSD", _ffi.IN_C64, precision="f32")
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+@pytest.mark.parametrize("shard", [None, (300, 1000)])
+def test_pipelined_host_batch_equals_single_shot(prec, shard, monkeypatch):
+    """large host batches cross PCIe in chunks while earlier chunks are transformed (kspec_zerospan_batch); every output must
+    equal the one-shot path: here 300 scans in chunks of 64 (the chunk size is an environment knob for this test)"""
+    F, S, r, n = 512, 4096, 0.5, 300
+    win = O.window_table("hanning", F)
+    x = synth.tones_noise(n * S, seed=77)
+    rng = np.random.default_rng(3)
+    adj = rng.normal(size=F) * 0.1
+    state = (rng.normal(size=F) - 30, rng.normal(size=F) - 60, rng.normal(size=F) - 45)
+    kw = dict(adj=adj, rows="db", want_hm=True)
+    if shard is not None:
+        kw.update(scan_index_base=shard[0], n_scans_total=shard[1])
+    else:
+        kw.update(state=state)
+    with Plan(F, S, r, win, "AVG", _ffi.IN_C64, precision=prec) as plan:
+        one = plan.zerospan_batch(x, n, 19.1, 128, "MAX", **kw)
+        launches0 = plan.launch_count()
+        monkeypatch.setenv("KSPEC_PIPELINE_CHUNK_BYTES", str(64 * S * 8))
+        piped = plan.zerospan_batch(x, n, 19.1, 128, "MAX", **kw)
+        assert plan.launch_count() - launches0 >= 5 * 2            # five parts: engine + stats each
+    assert np.array_equal(piped["rows"], one["rows"]) and np.array_equal(piped["hm_rows"], one["hm_rows"])
+    for k in ("max", "min"):
+        assert np.array_equal(piped[k], one[k]), k
+    assert np.max(np.abs(piped["avg"] - one["avg"])) < 1e-9
+    if shard is None and prec == "f64":
+        lin = [O.curscan(x[k * S:(k + 1) * S].astype(np.complex128), F, r, win, "AVG") for k in range(n)]
+        ref = O.zerospan(lin, 19.1, 128, "MAX", adj=adj, state=state)
+        for k, kk in (("rows", "cur_rows"), ("hm_rows", "hm_rows"), ("max", "max"), ("min", "min"), ("avg", "avg")):
+            assert np.max(np.abs(piped[k] - ref[kk])) < F64_TOL, k
