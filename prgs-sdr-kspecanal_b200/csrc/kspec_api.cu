@@ -276,6 +276,8 @@ int kspec_plan_create(kspec_plan** out, int fftSize, int64_t fullSize, double no
         const char* fb = getenv("KSPEC_FORCE_BLUESTEIN");
         if (pl->path == KSPEC_PATH_BLUESTEIN && fftSize > 4096 && !(fb && fb[0] == '1') && mixedradix_split(fftSize, &n1, &n2))
             pl->path = KSPEC_PATH_MIXEDRADIX;
+        const char* fm = getenv("KSPEC_FORCE_MIXED");
+        if (pl->path == KSPEC_PATH_FOURSTEP && fm && fm[0] == '1' && mixedradix_split(fftSize, &n1, &n2)) pl->path = KSPEC_PATH_MIXEDRADIX;
     }
 
     // frame offsets: int(i*F*r) with the product evaluated left to right in float64 (K:368, K:386-390)

@@ -29,6 +29,9 @@ CONFIGS = [
     ("cfg5a scan 4096 ones r=0.1 f64", 4096, "ones", 0.1, "AVG", "f64", 1024, "c64"),
     ("reference default 16384 ones r=0.1 f32", 16384, "ones", 0.1, "AVG", "f32", 512, "c64"),
     ("cfg4 2^21 ones MAX r=0.1 (four-step) f64", 1 << 21, "ones", 0.1, "MAX", "f64", 4, "c64"),
+    ("cfg4 2^21 ones MAX r=0.1 (mixed radix engine, forced) f64", 1 << 21, "ones", 0.1, "MAX", "f64", 4, "c64", {"KSPEC_FORCE_MIXED": "1"}),
+    ("reference default 16384 ones r=0.1 (four-step) f64", 16384, "ones", 0.1, "AVG", "f64", 512, "c64"),
+    ("reference default 16384 ones r=0.1 (mixed radix engine, forced) f64", 16384, "ones", 0.1, "AVG", "f64", 512, "c64", {"KSPEC_FORCE_MIXED": "1"}),
     ("cfg5b 2400000 ones r=0.1 (mixed radix 1500x1600) f64", 2400000, "ones", 0.1, "AVG", "f64", 4, "c64"),
     ("cfg5b 2400000 ones r=0.1 (Bluestein 2^23, forced) f64", 2400000, "ones", 0.1, "AVG", "f64", 2, "c64", {"KSPEC_FORCE_BLUESTEIN": "1"}),
     ("48000 hanning r=0.5 (mixed radix 200x240) f64", 48000, "hanning", 0.5, "AVG", "f64", 256, "c64"),
