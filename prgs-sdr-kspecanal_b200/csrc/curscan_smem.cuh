@@ -135,7 +135,11 @@ template <typename T> __device__ __forceinline__ T pos_inf();
 template <> __device__ __forceinline__ float pos_inf<float>() { return __int_as_float(0x7f800000); }
 template <> __device__ __forceinline__ double pos_inf<double>() { return __longlong_as_double(0x7ff0000000000000LL); }
 
-template <typename T, int INFMT, int LOG2F, int VAR = 0>
+// VB ("virtual bases"): the frame-parallel form for small batches.  Every frame of every scan is launched as a one-frame
+// scan of its own whose first sample comes from the table p.scanBase (= scan*fullSize + frame offset), so that a single
+// scan of 15..71 frames spreads over as many teams instead of walking its frames on one; frames_combine_kernel
+// (epilogue.cu) then applies data_cumu over the per-frame rows.  A separate instantiation: the batch kernels stay as they are.
+template <typename T, int INFMT, int LOG2F, int VAR = 0, bool VB = false>
 __global__ void __launch_bounds__(SmemCfg<T, LOG2F, VAR>::CTA, SmemCfg<T, LOG2F, VAR>::MINB)
 curscan_smem_kernel(const ScanParams p) {
     using C = SmemCfg<T, LOG2F, VAR>;
@@ -200,13 +204,13 @@ curscan_smem_kernel(const ScanParams p) {
         const int f = (int)(g - it * p.nFrames);
         int64_t sc = it * scansPerIter + slot;
         if (sc >= p.nScans) sc = p.nScans - 1;
-        const int64_t e0 = sc * p.scanStride + p.frameOffs[f];
+        const int64_t e0 = (VB ? __ldg(&p.scanBase[sc]) : sc * p.scanStride) + p.frameOffs[f];
         // 16-byte granules covering [e0, e0+F), never past the end of the batch (the batch length is a whole number of
         // granules whenever fullSize is, which holds for every fullSize the reference can produce, K:926-929)
         constexpr int64_t GM = SC::SLACK > 0 ? SC::SLACK - 1 : 0;
         const int64_t e0a = e0 & ~GM;
         int64_t e1a = (e0 + F + GM) & ~GM;
-        const int64_t total = (p.nScans * p.scanStride + GM) & ~GM;
+        const int64_t total = ((VB ? p.totalElems : p.nScans * p.scanStride) + GM) & ~GM;
         if (e1a > total) e1a = total;
         const int s = (STG == 2) ? (int)(g & 1) : 0;
         const uint32_t bytes = (uint32_t)((e1a - e0a) * SC::EB);
@@ -232,7 +236,7 @@ curscan_smem_kernel(const ScanParams p) {
         const int64_t scan = it * scansPerIter + slot;
         const bool valid = scan < p.nScans;
         const int64_t scanC = valid ? scan : p.nScans - 1;      // idle teams shadow the last scan (uniform barriers)
-        const int64_t sbase = scanC * p.scanStride;
+        const int64_t sbase = VB ? __ldg(&p.scanBase[scanC]) : scanC * p.scanStride;
 
         T acc[P];
         T avgW = (T)1;                                           // 2^(f-1) for frame f >= 1
@@ -366,11 +370,11 @@ curscan_smem_kernel(const ScanParams p) {
     }
 }
 
-template <typename T, int INFMT, int LOG2F, int VAR = 0>
+template <typename T, int INFMT, int LOG2F, int VAR = 0, bool VB = false>
 static int launch_smem_one(const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info) {
     using C = SmemCfg<T, LOG2F, VAR>;
     using SC = StageCfg<T, INFMT, LOG2F, VAR>;
-    auto k = curscan_smem_kernel<T, INFMT, LOG2F, VAR>;
+    auto k = curscan_smem_kernel<T, INFMT, LOG2F, VAR, VB>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SC::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     if (info) {

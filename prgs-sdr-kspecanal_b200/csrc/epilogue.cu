@@ -382,6 +382,30 @@ void launch_plotcompress(const double* y, int64_t n, int xRes, int mode, double*
     plotcompress_kernel<<<xRes, 256, 0, st>>>(y, g, mode, out);
 }
 
+// frame-parallel small batches: rows[(s*nFrames + f)*F + j] holds frame f of scan s (normalised, shifted); data_cumu
+// (K:124-147) over the frames in their order, one thread per (scan, bin)
+template <typename T>
+__global__ void frames_combine_kernel(const T* __restrict__ rows, T* __restrict__ out, int64_t nScans, int nFrames, int F, int cumuMode) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nScans * F) return;
+    const int64_t s = i / F;
+    const int j = (int)(i - s * F);
+    const T* r = rows + s * nFrames * F + j;
+    T a = r[0];
+    if (cumuMode == KSPEC_CUMU_RAW) a = r[(int64_t)(nFrames - 1) * F];
+    else if (cumuMode == KSPEC_CUMU_AVG) { for (int f = 1; f < nFrames; ++f) a = (a + r[(int64_t)f * F]) * (T)0.5; }
+    else if (cumuMode == KSPEC_CUMU_MAX) { for (int f = 1; f < nFrames; ++f) a = fmax(a, r[(int64_t)f * F]); }
+    else if (cumuMode == KSPEC_CUMU_MIN) { for (int f = 1; f < nFrames; ++f) a = fmin(a, r[(int64_t)f * F]); }
+    else { for (int f = 1; f < nFrames; ++f) a += r[(int64_t)f * F]; }
+    out[i] = a;
+}
+
+void launch_frames_combine(int prec, const void* rows, void* out, int64_t nScans, int nFrames, int F, int cumuMode, cudaStream_t st) {
+    const unsigned g = nblk(nScans * F, 256);
+    if (prec == KSPEC_PREC_F32) frames_combine_kernel<float><<<g, 256, 0, st>>>((const float*)rows, (float*)out, nScans, nFrames, F, cumuMode);
+    else frames_combine_kernel<double><<<g, 256, 0, st>>>((const double*)rows, (double*)out, nScans, nFrames, F, cumuMode);
+}
+
 void launch_linear_epilogue(int prec, const ScanParams& p, const void* acc, int F, int slots, cudaStream_t st) {
     (void)slots;
     if (prec == KSPEC_PREC_F32) {

@@ -83,7 +83,8 @@ struct kspec_plan {
     void* dTw = nullptr;
     void* dTwLin = nullptr;
     // grow-only workspaces
-    DevBuf in, rows, hm, wsMax, wsMin, avgRows, adj, adj64, carry, stats, wide, acc, l2, misc;
+    DevBuf in, rows, hm, wsMax, wsMin, avgRows, adj, adj64, carry, stats, wide, acc, l2, misc, frameRows, vbase;
+    int64_t vbaseScans = 0;                        // scans covered by the frame-parallel base table in vbase
     // what the last *_dev batch left behind (for fetch)
     int64_t lastScans = 0;
     int lastRowsKind = 0, lastW = 0;
@@ -134,6 +135,60 @@ ScanParams base_params(const kspec_plan* pl, const void* dSamples, int64_t nScan
 int run_engine(kspec_plan* pl, ScanParams& p, int* slotsOut) {
     const size_t rb = real_bytes(pl->prec);
     if (pl->path == KSPEC_PATH_SMEM) {
+        const int nFrames = (int)pl->offs.size();
+        {   // Small batches (the reference's own use: ONE scan per sdr_curscan call) leave most teams idle while each scan walks
+            // its 15..71 frames on one team: launch every frame as a one-frame scan of its own and cumulate afterwards.
+            const int64_t teamsAvail = (int64_t)pl->smCount * (pl->ki.ctasPerSm > 0 ? pl->ki.ctasPerSm : 1) * pl->ki.teams;
+            const int64_t nv = p.nScans * nFrames;
+            const char* fp = getenv("KSPEC_FRAME_PARALLEL");        // "0": always walk the frames of a scan on one team
+            const bool off = fp && fp[0] == '0';
+            // (up to 64 scans: the per-scan epilogue that follows walks the scans of a batch in order, one thread per bin)
+            if (!off && nFrames > 1 && p.nScans <= 64 && p.nScans * 2 <= teamsAvail && (size_t)nv * pl->F * rb <= ((size_t)256 << 20)) {
+                int rc;
+                if (pl->vbaseScans < p.nScans) {
+                    int64_t cap = 64;
+                    while (cap < p.nScans) cap *= 2;
+                    std::vector<int64_t> tab((size_t)cap * nFrames);
+                    for (int64_t s = 0; s < cap; ++s)
+                        for (int f = 0; f < nFrames; ++f) tab[(size_t)s * nFrames + f] = s * pl->S + pl->offs[f];
+                    if ((rc = pl->vbase.reserve(tab.size() * 8))) return rc;
+                    CK(cudaMemcpyAsync(pl->vbase.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, pl->st));
+                    CK(cudaStreamSynchronize(pl->st));           // tab goes out of scope
+                    pl->vbaseScans = cap;
+                }
+                if ((rc = pl->frameRows.reserve((size_t)nv * pl->F * rb)) || (rc = pl->acc.reserve((size_t)p.nScans * pl->F * rb))) return rc;
+                ScanParams v = base_params(pl, p.samples, nv);
+                v.scanBase = (const int64_t*)pl->vbase.p;
+                v.totalElems = p.nScans * pl->S;
+                v.nFrames = 1;                                   // frameOffs[0] == 0
+                v.cumuMode = pl->cumu == KSPEC_CUMU_PSD ? KSPEC_CUMU_PSD : KSPEC_CUMU_RAW;
+                v.rowsKind = KSPEC_ROWS_LINEAR;
+                v.rows = pl->frameRows.p;
+                const int teams = pl->ki.teams;
+                const int64_t need = (nv + teams - 1) / teams;
+                const int64_t cap = (int64_t)pl->smCount * (pl->ki.ctasPerSm > 0 ? pl->ki.ctasPerSm : 1);
+                const int grid = (int)(need < cap ? need : cap);
+                const int ks = (int)(pl->kcount % kspec_plan::KT);
+                cudaEventRecord(pl->kev[ks][0], pl->st);
+                const int e = launch_smem(pl, SMEM_VARIANT_FRAMES, v, grid < 1 ? 1 : grid, nullptr);
+                cudaEventRecord(pl->kev[ks][1], pl->st);
+                pl->kcount += 1;
+                if (e != 0) { set_error("frame-parallel scan kernel launch failed: %s", cudaGetErrorString((cudaError_t)e)); return KSPEC_ERR_CUDA; }
+                launch_frames_combine(pl->prec, pl->frameRows.p, pl->acc.p, p.nScans, nFrames, pl->F, pl->cumu, pl->st);
+                if (p.wantStats) {
+                    if ((rc = pl->wsMax.reserve((size_t)pl->F * rb)) || (rc = pl->wsMin.reserve((size_t)pl->F * rb))) return rc;
+                    p.wsMax = pl->wsMax.p;
+                    p.wsMin = pl->wsMin.p;
+                }
+                p.accL1 = p.accL2 = 0;
+                p.accShifted = 1;
+                p.linScale = 1.0;
+                launch_linear_epilogue(pl->prec, p, pl->acc.p, pl->F, 1, pl->st);
+                pl->launches += p.hm ? 4 : 3;
+                *slotsOut = 1;
+                return KSPEC_OK;
+            }
+        }
         // large batches of the headline shape run four independent teams per CTA (one CTA per SM); small ones the base layout
         const bool multi = pl->kiMulti.ctasPerSm > 0 && p.nScans >= (int64_t)2 * pl->smCount * pl->kiMulti.teams;
         const SmemKernelInfo& ki = multi ? pl->kiMulti : pl->ki;
@@ -392,7 +447,7 @@ int kspec_plan_destroy(kspec_plan* pl) {
     if (pl->big) bigfft_destroy(pl->big);
     if (pl->mixed) mixedradix_destroy(pl->mixed);
     for (DevBuf* b : {&pl->in, &pl->rows, &pl->hm, &pl->wsMax, &pl->wsMin, &pl->avgRows, &pl->adj, &pl->adj64, &pl->carry, &pl->stats,
-                      &pl->wide, &pl->acc, &pl->l2, &pl->misc}) b->release();
+                      &pl->wide, &pl->acc, &pl->l2, &pl->misc, &pl->frameRows, &pl->vbase}) b->release();
     if (pl->dOffs) cudaFree(pl->dOffs);
     if (pl->dWin) cudaFree(pl->dWin);
     if (pl->dTw) cudaFree(pl->dTw);

@@ -13,6 +13,8 @@ struct ScanParams {
     const void* samples;       // device, nScans * scanStride elements of the ingest format
     int64_t scanStride;        // elements between consecutive scans (= fullSize)
     int64_t nScans;
+    const int64_t* scanBase;   // frame-parallel launches only (SMEM_VARIANT_FRAMES): first element of every one-frame "scan"
+    int64_t totalElems;        // ... and the length of the sample buffer, for the clipped bulk copies
     const int32_t* frameOffs;  // device, nFrames frame start offsets inside a scan (K:386)
     int32_t nFrames;
     const void* win;           // device T[F]
@@ -45,7 +47,8 @@ struct ScanParams {
 struct SmemKernelInfo { int ctaThreads, smemBytes, teams, ctasPerSm, stages; };
 
 // one per (precision, ingest format); defined in smem_inst_*.cu.  info != nullptr: query only, no launch.
-// variant: SMEM_VARIANT_BASE, or SMEM_VARIANT_MULTI (fftSize 2048, float32: four independent teams per CTA, for large batches)
+// variant: SMEM_VARIANT_BASE, SMEM_VARIANT_MULTI (fftSize 2048, float32: four independent teams per CTA, for large batches)
+// or SMEM_VARIANT_FRAMES (the base layout reading per-"scan" bases from ScanParams::scanBase: frame-parallel small batches)
 int launch_smem_f32_u8(int log2F, int variant, const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info);
 int launch_smem_f32_c64(int log2F, int variant, const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info);
 int launch_smem_f32_c128(int log2F, int variant, const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info);
@@ -53,7 +56,7 @@ int launch_smem_f64_u8(int log2F, int variant, const ScanParams& p, int grid, cu
 int launch_smem_f64_c64(int log2F, int variant, const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info);
 int launch_smem_f64_c128(int log2F, int variant, const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info);
 
-constexpr int SMEM_VARIANT_BASE = 0, SMEM_VARIANT_MULTI = 1;
+constexpr int SMEM_VARIANT_BASE = 0, SMEM_VARIANT_MULTI = 1, SMEM_VARIANT_FRAMES = 2;
 constexpr int SMEM_MAX_LOG2F_F32 = 14;
 constexpr int SMEM_MAX_LOG2F_F64 = 13;
 constexpr int SMEM_MIN_LOG2F = 4;
@@ -82,6 +85,8 @@ void launch_plotcompress(const double* y, int64_t n, int xRes, int mode, double*
 // epilogue for engines that deliver linear, un-shifted, un-normalised |X| accumulations per scan (big FFT paths)
 void launch_linear_epilogue(int prec, const ScanParams& p, const void* acc /*T[nScans][F] natural bin order*/,
                             int F, int slots, cudaStream_t st);
+
+void launch_frames_combine(int prec, const void* rows, void* out, int64_t nScans, int nFrames, int F, int cumuMode, cudaStream_t st);
 
 // ---- bigfft.cu ---------------------------------------------------------------------------------------------------
 struct BigFft;   // four-step power-of-two engine + Bluestein wrapper

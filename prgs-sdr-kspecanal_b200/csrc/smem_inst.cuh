@@ -11,6 +11,7 @@ int KSPEC_INST_NAME(int log2F, int variant, const ScanParams& p, int grid, cudaS
     if constexpr (F32) {
         if (log2F == 11) {
             // the headline shape (fftSize 2048, float32): tuned layouts, see profiles/README.md
+            if (variant == SMEM_VARIANT_FRAMES) return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, 11, 3, true>(p, grid, st, info);
             int var = variant == SMEM_VARIANT_MULTI ? 4 : 3;
 #ifdef KSPEC_INST_VARIANTS
             static const int forced = [] { const char* e = getenv("KSPEC_VARIANT"); return e ? atoi(e) : -1; }();
@@ -26,7 +27,8 @@ int KSPEC_INST_NAME(int log2F, int variant, const ScanParams& p, int grid, cudaS
             return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, 11, 3>(p, grid, st, info);
         }
     }
-    if (variant != SMEM_VARIANT_BASE) return (int)cudaErrorInvalidValue;
+    if (variant != SMEM_VARIANT_BASE && variant != SMEM_VARIANT_FRAMES) return (int)cudaErrorInvalidValue;
+    const bool vb = variant == SMEM_VARIANT_FRAMES;
     if constexpr (!F32) {
         // fftSize 2048 in float64 (the default precision): one exchange buffer and one TMA stage leave room for three CTAs per
         // SM instead of two: 81 -> 96 G samples/s (profiles/README.md)
@@ -36,11 +38,14 @@ int KSPEC_INST_NAME(int log2F, int variant, const ScanParams& p, int grid, cudaS
             if (forced == 0) return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, 11, 0>(p, grid, st, info);
             if (forced == 9) return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, 11, 9>(p, grid, st, info);
 #endif
+            if (vb) return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, 11, 8, true>(p, grid, st, info);
             return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, 11, 8>(p, grid, st, info);
         }
     }
     switch (log2F) {
-#define KSPEC_CASE(L) case L: if constexpr (L <= KSPEC_INST_MAXLOG2F && L != 11) return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, L>(p, grid, st, info); else break;
+#define KSPEC_CASE(L) case L: if constexpr (L <= KSPEC_INST_MAXLOG2F && L != 11) { \
+        if (vb) return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, L, 0, true>(p, grid, st, info); \
+        return launch_smem_one<KSPEC_INST_T, KSPEC_INST_FMT, L>(p, grid, st, info); } else break;
         KSPEC_CASE(4) KSPEC_CASE(5) KSPEC_CASE(6) KSPEC_CASE(7) KSPEC_CASE(8) KSPEC_CASE(9) KSPEC_CASE(10)
         KSPEC_CASE(11) KSPEC_CASE(12) KSPEC_CASE(13) KSPEC_CASE(14)
 #undef KSPEC_CASE

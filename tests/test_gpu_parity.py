@@ -56,7 +56,10 @@ def _cap(g):
     ("g3_zerospan_8192_kaiser.npz", "f64"), ("g3_zerospan_8192_kaiser.npz", "auto"),
     ("g4_zerospan_32768_ones_max_u8.npz", "auto"),
 ])
-def test_zerospan_golden(name, prec):
+@pytest.mark.parametrize("frame_parallel", ["1", "0"])
+def test_zerospan_golden(name, prec, frame_parallel, monkeypatch):
+    # small batches spread the frames of a scan over teams (frame-parallel form); "0" forces the batch form of the kernel
+    monkeypatch.setenv("KSPEC_FRAME_PARALLEL", frame_parallel)
     g = load_golden(name)
     p = g["params"]
     F, S, n = p["fftSize"], p["fullSize"], p["nScans"]
@@ -73,7 +76,7 @@ def test_zerospan_golden(name, prec):
     for k in range(n):
         assert_db_close(lin[k], g["lin_rows"][k], tol, "scan %d" % k, f32=plan.precision == "f32")
         assert int(np.argmax(lin[k])) == int(np.argmax(g["lin_rows"][k]))   # peak bin: bit-exact
-    assert np.array_equal(one, lin[0])
+    assert np.max(np.abs(db(one) - db(lin[0]))) < 1e-5
     assert np.max(np.abs(out["rows"] - g["db_rows"])) < tol
     assert np.max(np.abs(out["max"] - g["fft_max"])) < tol
     assert np.max(np.abs(out["min"] - g["fft_min"])) < tol
@@ -85,7 +88,9 @@ def test_zerospan_golden(name, prec):
 @pytest.mark.parametrize("name", ["g2_scan_64_r100.npz", "g2_scan_64_r050.npz", "g5a_fmscan_4096_u8.npz",
                                   "g5b_scan_1200_cur.npz", "g5b_scan_1200_raw.npz"])
 @pytest.mark.parametrize("prec", ["f32", "f64"])
-def test_scan_golden(name, prec):
+@pytest.mark.parametrize("frame_parallel", ["1", "0"])
+def test_scan_golden(name, prec, frame_parallel, monkeypatch):
+    monkeypatch.setenv("KSPEC_FRAME_PARALLEL", frame_parallel)
     g = load_golden(name)
     p = g["params"]
     if p["fftSize"] == 1200:
@@ -119,7 +124,9 @@ def test_scan_golden(name, prec):
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("log2f", [4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14])
 @pytest.mark.parametrize("prec", ["f32", "f64"])
-def test_curscan_all_sizes(log2f, prec):
+@pytest.mark.parametrize("frame_parallel", ["1", "0"])
+def test_curscan_all_sizes(log2f, prec, frame_parallel, monkeypatch):
+    monkeypatch.setenv("KSPEC_FRAME_PARALLEL", frame_parallel)
     if prec == "f64" and log2f > 13:
         pytest.skip("float64 frames above 8192 use the multi-pass engine")
     F = 1 << log2f
@@ -704,10 +711,11 @@ def test_pipelined_host_batch_equals_single_shot(prec, shard, monkeypatch):
         monkeypatch.setenv("KSPEC_PIPELINE_CHUNK_BYTES", str(64 * S * 8))
         piped = plan.zerospan_batch(x, n, 19.1, 128, "MAX", **kw)
         assert plan.launch_count() - launches0 >= 5 * 2            # five parts: engine + stats each
-    assert np.array_equal(piped["rows"], one["rows"]) and np.array_equal(piped["hm_rows"], one["hm_rows"])
-    for k in ("max", "min"):
-        assert np.array_equal(piped[k], one[k]), k
-    assert np.max(np.abs(piped["avg"] - one["avg"])) < 1e-9
+    # the 64-scan parts take the frame-parallel form of the kernel, the one-shot batch the batch form: same values up to the
+    # rounding of the working precision
+    eq = 1e-4 if prec == "f32" else 1e-9
+    for k in ("rows", "hm_rows", "max", "min", "avg"):
+        assert np.max(np.abs(piped[k] - one[k])) < eq, k
     if shard is None and prec == "f64":
         lin = [O.curscan(x[k * S:(k + 1) * S].astype(np.complex128), F, r, win, "AVG") for k in range(n)]
         ref = O.zerospan(lin, 19.1, 128, "MAX", adj=adj, state=state)
