@@ -124,6 +124,25 @@ def profiled_traffic():
     return (tot or None), os.path.relpath(files[-1], ROOT)
 
 
+def profiled_pipes():
+    """what bounds the fused kernel instead of HBM (SURVEY 8d asks for it next to the HBM fraction): busy share of the
+    FP32 (FMA) pipe, the shared-memory / L1 data pipe and the issue slots, from the same committed ncu capture"""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_*final*.csv")))
+    if not files:
+        return None
+    want = {"sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active": "fp32_fma_pipe_pct",
+            "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed": "shared_l1_data_pipe_pct",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_slots_pct"}
+    out = {}
+    for row in csv.reader(open(files[-1])):
+        if row and row[0] in want:
+            out[want[row[0]]] = round(float(row[2]), 1)
+    out["source"] = os.path.relpath(files[-1], ROOT)
+    return out
+
+
 def bind_to_gpu_numa_node(local):
     """pin this rank (and therefore its pinned host buffers, first touch) to the NUMA node of its GPU: with 8 ranks the
     end-to-end leg is bound by host memory / PCIe root complexes, not by the GPUs"""
@@ -365,7 +384,7 @@ def run_ours(args):
                        "frames_per_s": value * 1e6 * info.n_frames / S, "parallelism": "scan-range shards x%d" % world, "numa_node_rank0": numa,
                        "cta_threads": info.cta_threads, "ctas_per_sm": info.ctas_per_sm, "smem_bytes": info.smem_bytes},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": profiled_traffic()[0], "traffic_source": profiled_traffic()[1],
+                         "traffic": profiled_traffic()[0], "traffic_source": profiled_traffic()[1], "other_pipes": profiled_pipes(),
                          "peak_source": peak_src, "kernel": "curscan_smem_kernel<%s,C64,11>" % ("float" if plan.precision == "f32" else "double"), "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": algorithmic_bytes(N_SCANS)},
             "cpu_baseline": {"value": cpu_v, "unit": "Msamples/s", "cores": cores, "kind": "port", "single_core_value": cpu_1,
