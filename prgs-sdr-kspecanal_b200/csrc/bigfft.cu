@@ -211,14 +211,14 @@ int bigfft_run(BigFft* b, const void* samples, int64_t scanStride, int64_t nScan
         const void* smp = reinterpret_cast<const unsigned char*>(samples) + (size_t)s0 * scanStride * eb;
         // pass 1: columns of every (zero padded) frame of the chunk
         if (b->inFmt == KSPEC_IN_U8_IQ) {
-            OpColsIn<KSPEC_IN_U8_IQ> op{g, smp, scanStride, b->dOffs, nFrames, b->dWin, blue ? b->dChirp : nullptr, b->dTwM, b->dZ, b->u8off, b->u8scale};
-            e = big_cols_in(b->inFmt, b->l1, &op, b->dTw1, nfs * L2, b->smCount, st);
+            OpColsIn<KSPEC_IN_U8_IQ, false> op{g, smp, scanStride, b->dOffs, nFrames, b->dWin, blue ? b->dChirp : nullptr, b->dTwM, b->dZ, b->u8off, b->u8scale};
+            e = big_cols_in(b->inFmt, blue ? 1 : 0, b->l1, &op, b->dTw1, nfs * L2, b->smCount, st);
         } else if (b->inFmt == KSPEC_IN_C64) {
-            OpColsIn<KSPEC_IN_C64> op{g, smp, scanStride, b->dOffs, nFrames, b->dWin, blue ? b->dChirp : nullptr, b->dTwM, b->dZ, b->u8off, b->u8scale};
-            e = big_cols_in(b->inFmt, b->l1, &op, b->dTw1, nfs * L2, b->smCount, st);
+            OpColsIn<KSPEC_IN_C64, false> op{g, smp, scanStride, b->dOffs, nFrames, b->dWin, blue ? b->dChirp : nullptr, b->dTwM, b->dZ, b->u8off, b->u8scale};
+            e = big_cols_in(b->inFmt, blue ? 1 : 0, b->l1, &op, b->dTw1, nfs * L2, b->smCount, st);
         } else {
-            OpColsIn<KSPEC_IN_C128> op{g, smp, scanStride, b->dOffs, nFrames, b->dWin, blue ? b->dChirp : nullptr, b->dTwM, b->dZ, b->u8off, b->u8scale};
-            e = big_cols_in(b->inFmt, b->l1, &op, b->dTw1, nfs * L2, b->smCount, st);
+            OpColsIn<KSPEC_IN_C128, false> op{g, smp, scanStride, b->dOffs, nFrames, b->dWin, blue ? b->dChirp : nullptr, b->dTwM, b->dZ, b->u8off, b->u8scale};
+            e = big_cols_in(b->inFmt, blue ? 1 : 0, b->l1, &op, b->dTw1, nfs * L2, b->smCount, st);
         }
         *launches += 1;
         if (e) break;

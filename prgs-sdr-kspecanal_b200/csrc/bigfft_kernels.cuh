@@ -26,82 +26,96 @@ struct BigGeom {
 };
 
 // ---- pass ops ---------------------------------------------------------------------------------------------------
-// Every op provides   cd load(int64_t q, int e)   and   void store(int64_t q, int k, cd v)   for batch item q.
+// Every op provides   Ctx begin(int64_t q)   (the per-item index arithmetic, done once: the 64-bit division by nFrames used to be
+// repeated for each of a thread's 16 elements and kept their loads from being issued back to back),
+// cd load(const Ctx&, int e)   and   void store(const Ctx&, int k, cd v)   for batch item q.
 // One launch covers every frame of every scan of a chunk: q = fs * L2 + n2 (column passes) or fs * L1 + k1 (row passes),
 // fs = scan * nFrames + frame; the work vectors Z and P hold one M-point slab per fs.
 
 // column pass, first transform: gather the frame (fused ingest, window, optional chirp, zero padding)
-template <int INFMT> struct OpColsIn {
+// BLUE: chirp multiply and zero padding (n >= F).  Both forms are branch-free so that a thread's 16 element loads issue back
+// to back: with a per-element branch every load sat in its own basic block and cost a full round trip.
+template <int INFMT, bool BLUE> struct OpColsIn {
     BigGeom g;
     const void* samples; int64_t scanStride; const int64_t* offs; int nFrames;
     const double* win; const cd* chirp;   // chirp == nullptr for the plain four-step transform
     const cd* twM; cd* Z;
     double u8off, u8scale;
-    __device__ __forceinline__ cd load(int64_t q, int e) const {
+    struct Ctx { int64_t base, n2, zbase; };       // first sample of the frame, column, first element of the frame's slab
+    __device__ __forceinline__ Ctx begin(int64_t q) const {
         const int64_t fs = q >> g.l2, n2 = q & (((int64_t)1 << g.l2) - 1);
-        const int64_t n = ((int64_t)e << g.l2) + n2;
-        if (n >= g.F) return make_double2(0.0, 0.0);
         const int64_t s = fs / nFrames;
-        const int64_t base = s * scanStride + __ldg(&offs[fs - s * nFrames]);
-        cd v = Ingest<double, INFMT>::load(samples, base + n, __ldg(&win[n]), u8off, u8scale);
-        if (chirp) v = cmul(v, __ldg(&chirp[n]));
-        return v;
+        return Ctx{s * scanStride + __ldg(&offs[fs - s * nFrames]), n2, fs * g.M};
     }
-    __device__ __forceinline__ void store(int64_t q, int k, cd v) const {
-        const int64_t fs = q >> g.l2, n2 = q & (((int64_t)1 << g.l2) - 1);
-        Z[fs * g.M + ((int64_t)k << g.l2) + n2] = cmul(v, __ldg(&twM[n2 * k]));
+    __device__ __forceinline__ cd load(const Ctx& c, int e) const {
+        const int64_t n = ((int64_t)e << g.l2) + c.n2;
+        if constexpr (!BLUE) {
+            return Ingest<double, INFMT>::load(samples, c.base + n, __ldg(&win[n]), u8off, u8scale);
+        } else {
+            const bool in = n < g.F;
+            const int64_t m = in ? n : 0;
+            const cd v = cmul(Ingest<double, INFMT>::load(samples, c.base + m, __ldg(&win[m]), u8off, u8scale), __ldg(&chirp[m]));
+            return in ? v : make_double2(0.0, 0.0);
+        }
+    }
+    __device__ __forceinline__ void store(const Ctx& c, int k, cd v) const {
+        Z[c.zbase + ((int64_t)k << g.l2) + c.n2] = cmul(v, __ldg(&twM[c.n2 * k]));
     }
 };
 
 // column pass on a natural-order device vector (precomputing V; single slab)
 struct OpColsPlain {
     BigGeom g; const cd* X; const cd* twM; cd* Z;
-    __device__ __forceinline__ cd load(int64_t q, int e) const { return X[((int64_t)e << g.l2) + q]; }
-    __device__ __forceinline__ void store(int64_t q, int k, cd v) const { Z[((int64_t)k << g.l2) + q] = cmul(v, __ldg(&twM[q * k])); }
+    typedef int64_t Ctx;
+    __device__ __forceinline__ Ctx begin(int64_t q) const { return q; }
+    __device__ __forceinline__ cd load(const Ctx& q, int e) const { return X[((int64_t)e << g.l2) + q]; }
+    __device__ __forceinline__ void store(const Ctx& q, int k, cd v) const { Z[((int64_t)k << g.l2) + q] = cmul(v, __ldg(&twM[q * k])); }
 };
 
 // column pass of the SECOND Bluestein transform: its input P sits in the row pass's output layout [k1*L2 + k2]
 struct OpColsMid {
     BigGeom g; const cd* P; const cd* twM; cd* Z;
-    __device__ __forceinline__ cd load(int64_t q, int e) const {
+    struct Ctx { int64_t zbase, n2, loc0; };
+    __device__ __forceinline__ Ctx begin(int64_t q) const {
         // element n = e*L2 + n2 of the natural-order vector lives at (n mod L1)*L2 + n div L1   (L2 >= L1)
         const int64_t fs = q >> g.l2, n2 = q & (((int64_t)1 << g.l2) - 1);
         const int64_t L1m = ((int64_t)1 << g.l1) - 1;
-        const int64_t loc = ((n2 & L1m) << g.l2) + ((int64_t)e << (g.l2 - g.l1)) + (n2 >> g.l1);
-        return P[fs * g.M + loc];
+        return Ctx{fs * g.M, n2, fs * g.M + ((n2 & L1m) << g.l2) + (n2 >> g.l1)};
     }
-    __device__ __forceinline__ void store(int64_t q, int k, cd v) const {
-        const int64_t fs = q >> g.l2, n2 = q & (((int64_t)1 << g.l2) - 1);
-        Z[fs * g.M + ((int64_t)k << g.l2) + n2] = cmul(v, __ldg(&twM[n2 * k]));
+    __device__ __forceinline__ cd load(const Ctx& c, int e) const { return P[c.loc0 + ((int64_t)e << (g.l2 - g.l1))]; }
+    __device__ __forceinline__ void store(const Ctx& c, int k, cd v) const {
+        Z[c.zbase + ((int64_t)k << g.l2) + c.n2] = cmul(v, __ldg(&twM[c.n2 * k]));
     }
 };
 
 // row pass storing the spectrum as is, layout [k1*L2 + k2] (precomputing V; single slab)
 struct OpRowsPlain {
     BigGeom g; const cd* Z; cd* out;
-    __device__ __forceinline__ cd load(int64_t q, int e) const { return Z[(q << g.l2) + e]; }
-    __device__ __forceinline__ void store(int64_t q, int k, cd v) const { out[(q << g.l2) + k] = v; }
+    typedef int64_t Ctx;
+    __device__ __forceinline__ Ctx begin(int64_t q) const { return q << g.l2; }
+    __device__ __forceinline__ cd load(const Ctx& o, int e) const { return Z[o + e]; }
+    __device__ __forceinline__ void store(const Ctx& o, int k, cd v) const { out[o + k] = v; }
 };
 
 // row pass of the first Bluestein transform: P = conj(U . V)
 struct OpRowsMul {
     BigGeom g; const cd* Z; const cd* V; cd* P;
-    __device__ __forceinline__ cd load(int64_t q, int e) const {
+    struct Ctx { int64_t zrow, vrow; };            // first element of the row in the slab / in V
+    __device__ __forceinline__ Ctx begin(int64_t q) const {
         const int64_t fs = q >> g.l1, k1 = q & (((int64_t)1 << g.l1) - 1);
-        return Z[fs * g.M + (k1 << g.l2) + e];
+        return Ctx{fs * g.M + (k1 << g.l2), k1 << g.l2};
     }
-    __device__ __forceinline__ void store(int64_t q, int k, cd v) const {
-        const int64_t fs = q >> g.l1, k1 = q & (((int64_t)1 << g.l1) - 1);
-        const int64_t i = (k1 << g.l2) + k;
-        P[fs * g.M + i] = cconj(cmul(v, __ldg(&V[i])));
-    }
+    __device__ __forceinline__ cd load(const Ctx& c, int e) const { return Z[c.zrow + e]; }
+    __device__ __forceinline__ void store(const Ctx& c, int k, cd v) const { P[c.zrow + k] = cconj(cmul(v, __ldg(&V[c.vrow + k]))); }
 };
 
 // contiguous batched transform on device vectors (V for the small Bluestein, self tests)
 struct OpPlain {
     int l; const cd* X; cd* Y;
-    __device__ __forceinline__ cd load(int64_t q, int e) const { return X[(q << l) + e]; }
-    __device__ __forceinline__ void store(int64_t q, int k, cd v) const { Y[(q << l) + k] = v; }
+    typedef int64_t Ctx;
+    __device__ __forceinline__ Ctx begin(int64_t q) const { return q << l; }
+    __device__ __forceinline__ cd load(const Ctx& o, int e) const { return X[o + e]; }
+    __device__ __forceinline__ void store(const Ctx& o, int k, cd v) const { Y[o + k] = v; }
 };
 
 // ---- one kernel for all passes: a team of NT threads transforms batch item q ---------------------------------------
@@ -123,15 +137,16 @@ team_fft_kernel(const Op op, const cd* __restrict__ tw, int64_t nBatch) {
         const int64_t q = it * perIter + (int64_t)blockIdx.x * TEAMS + team;
         const bool valid = q < nBatch;
         const int64_t qc = valid ? q : nBatch - 1;
+        const typename Op::Ctx ctx = op.begin(qc);
         cd b[P];
 #pragma unroll
-        for (int m = 0; m < P; ++m) b[m] = op.load(qc, tid + NT * m);
+        for (int m = 0; m < P; ++m) b[m] = op.load(ctx, tid + NT * m);
         butterflies<double, P, (1 << L0), false>(b, nullptr);
         fft_tail<double, LOG2L, LOG2P, false, C::DBUF, L0, 0, 0>(b, nullptr, tw, bufA, bufB, tid, sync);
         if constexpr (C::DBUF && (C::NX & 1)) { cd* t = bufA; bufA = bufB; bufB = t; }
         if (valid) {
 #pragma unroll
-            for (int m = 0; m < P; ++m) op.store(q, tid + NT * m, b[m]);
+            for (int m = 0; m < P; ++m) op.store(ctx, tid + NT * m, b[m]);
         }
     }
 }
@@ -314,7 +329,7 @@ static int launch_bluestein_smem(const BlueSmallParams& p, int smCount, cudaStre
 }
 
 // entry points of the separately compiled instantiation units
-int big_cols_in(int inFmt, int l1, const void* op, const cd* tw, int64_t nBatch, int smCount, cudaStream_t st);
+int big_cols_in(int inFmt, int blue, int l1, const void* op, const cd* tw, int64_t nBatch, int smCount, cudaStream_t st);
 int big_cols_plain(int l1, const OpColsPlain& op, const cd* tw, int64_t nBatch, int smCount, cudaStream_t st);
 int big_cols_mid(int l1, const OpColsMid& op, const cd* tw, int64_t nBatch, int smCount, cudaStream_t st);
 int big_rows_plain(int l2, const OpRowsPlain& op, const cd* tw, int64_t nBatch, int smCount, cudaStream_t st);

@@ -183,24 +183,22 @@ __global__ void __launch_bounds__(NT, 2) mr_cols_kernel(const MrColsParams p) {
         const int64_t base = s * p.scanStride + __ldg(&p.offs[fs - s * p.nFrames]);
 #pragma unroll 4
         for (int i = threadIdx.x; i < items; i += NT) {
+            // branch-free, so that the unrolled iterations' loads issue back to back (a ragged last tile re-reads column 0)
             const int line = i & (TC - 1), e = i >> lTC, n2 = c0 + line;
-            cd v = make_double2(0.0, 0.0);
-            if (n2 < N2) {
-                const int64_t n = (int64_t)e * N2 + n2;
-                v = Ingest<double, INFMT>::load(p.samples, base + n, __ldg(&p.win[n]), p.u8off, p.u8scale);
-            }
-            bufA[i] = v;
+            const bool in = n2 < N2;
+            const int64_t n = (int64_t)e * N2 + (in ? n2 : 0);
+            const cd v = Ingest<double, INFMT>::load(p.samples, base + n, __ldg(&p.win[n]), p.u8off, p.u8scale);
+            bufA[i] = in ? v : make_double2(0.0, 0.0);
         }
         __syncthreads();
         const cd* res = mr_transform<true, NT>(p.sc, bufA, bufB, stab, p.tabL);
 #pragma unroll 4
         for (int i = threadIdx.x; i < items; i += NT) {
             const int line = i & (TC - 1), k1 = i >> lTC, n2 = c0 + line;
-            if (n2 < N2) {
-                const int t = n2 * k1;                       // < F <= MR_MAX_LINE^2 < 2^31
-                const cd w = cmul(__ldg(&p.tabHi[t >> MR_TW_LO_BITS]), __ldg(&p.tabLo[t & ((1 << MR_TW_LO_BITS) - 1)]));
-                p.Z[fs * p.F + (int64_t)k1 * N2 + n2] = cmul(res[i], w);
-            }
+            const bool in = n2 < N2;
+            const int t = (in ? n2 : 0) * k1;                // < F <= MR_MAX_LINE^2 < 2^31
+            const cd w = cmul(__ldg(&p.tabHi[t >> MR_TW_LO_BITS]), __ldg(&p.tabLo[t & ((1 << MR_TW_LO_BITS) - 1)]));
+            if (in) p.Z[fs * p.F + (int64_t)k1 * N2 + n2] = cmul(res[i], w);
         }
         __syncthreads();
     }
@@ -232,7 +230,9 @@ __global__ void __launch_bounds__(NT, (MR_MAXA <= mr_maxa(MR_SMEM_STD, NT) ? 2 :
 #pragma unroll 4
             for (int i = threadIdx.x; i < items; i += NT) {
                 const int line = mr_div(i, p.sc.mL), e = i - line * N2, k1 = r0 + line;
-                bufA[i] = (k1 < N1) ? __ldg(&zf[(int64_t)k1 * N2 + e]) : make_double2(0.0, 0.0);
+                const bool in = k1 < N1;
+                const cd v = __ldg(&zf[(int64_t)(in ? k1 : 0) * N2 + e]);
+                bufA[i] = in ? v : make_double2(0.0, 0.0);
             }
             __syncthreads();
             const cd* res = mr_transform<false, NT>(p.sc, bufA, bufB, stab, p.tabL);
