@@ -124,7 +124,18 @@ __device__ __forceinline__ float kabs(float2 a) {
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s));
     return r;
 }
-__device__ __forceinline__ double kabs(double2 a) { return sqrt(a.x * a.x + a.y * a.y); }
+// |X| in float64.  The correctly rounded sqrt() costs ~8 FP64 operations plus a guarded slow path per bin and frame, one sixth
+// of the FP64 work of a kernel whose bound is the FP64 pipe.  Here: the hardware reciprocal-square-root seed (MUFU.RSQ64H,
+// relative error ~2^-22) and one Goldschmidt step: relative error ~2^-43 (5e-13 dB; the float64 engines are specified to
+// 1e-8 dB).  Exact zeros (a silent capture) stay zero.
+__device__ __forceinline__ double kabs(double2 a) {
+    const double p = a.x * a.x + a.y * a.y;
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(p));
+    const double g = p * r, h = 0.5 * r;
+    const double e = fma(-g, h, 0.5);
+    return p > 1e-290 ? fma(g, e, g) : 0.0;
+}
 
 // 10*log10(v) in the float32 fast mode: MUFU.LG2 (abs error 2^-22 in log2 near 1, 2 ulp elsewhere) -> < 2e-5 dB, far inside
 // the 1e-3 dB budget, for ~20 instructions less per bin than log10f.  0 -> -inf as numpy (K:109).
