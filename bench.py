@@ -364,6 +364,15 @@ def run_ours(args):
     h2d = N_SCANS * S * 8
     d2h = N_SCANS * XRES * 8 + 3 * F * 8
 
+    # supplementary: the same end-to-end call on the wire format of the reference's device, interleaved uint8 I/Q (2 B per
+    # sample: octave/load_rtlsdr.m:8-12; the conversion pyrtlsdr does on the host is fused into the first FFT stage here)
+    e2e_u8 = None
+    if world == 1:
+        try:
+            e2e_u8 = e2e_uint8_leg(win, S, host_out, args.steps)
+        except Exception as exc:                                    # never let the extra leg cost the headline line
+            e2e_u8 = {"error": str(exc)[:200]}
+
     if rank == 0:
         peak, peak_src = peaks()
         k_ms = float(np.mean(kt)) if kt else ms / args.steps
@@ -390,6 +399,7 @@ def run_ours(args):
             "cpu_baseline": {"value": cpu_v, "unit": "Msamples/s", "cores": cores, "kind": "port", "single_core_value": cpu_1,
                              "sample": "%d scans per process x %d processes (%.0f M IQ samples), best of 2, numpy float64 oracle port" % (640, cores, 640 * cores * S / 1e6)},
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e_uint8_iq": e2e_u8,
             "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line))
@@ -399,6 +409,33 @@ def run_ours(args):
     plan.dev_free(d_samples)
     plan.close()
     return 0
+
+
+def e2e_uint8_leg(win, S, host_out, steps):
+    """kspec_zerospan_batch on pinned interleaved uint8 I/Q of the same shape (supplementary; N = 1 only)"""
+    from kspec import _ffi, synth
+    from kspec.engine import Plan
+    plan = Plan(F, S, R_NONOVERLAP, win, "AVG", _ffi.IN_U8_IQ, precision=os.environ.get("KSPEC_BENCH_PRECISION", "f32"))
+    pinned = _ffi.PinnedBuffer(N_SCANS * S * 2)
+    host = pinned.view(np.uint8)
+    base = synth.to_u8_iq(synth.tones_noise(BASE_SCANS * S, seed=1).astype(np.complex128))
+    for i in range(N_SCANS // BASE_SCANS):
+        host[i * len(base):(i + 1) * len(base)] = base
+
+    def step():
+        return plan.zerospan_batch(host, N_SCANS, GAIN, XRES, "MAX", rows=None, want_hm=True, out=host_out)
+
+    step()
+    plan.sync()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    plan.sync()
+    dt = time.perf_counter() - t0
+    plan.close()
+    pinned.free()
+    return {"value": N_SCANS * S * steps / dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": N_SCANS * S * 2,
+            "d2h_bytes_per_step": N_SCANS * XRES * 8 + 3 * F * 8}
 
 
 def _max_over_ranks(v, dist, local):
