@@ -26,6 +26,26 @@ def test_header_and_binding_agree():
     assert sorted(_ffi.SIGNATURES) == syms
 
 
+def header_enums():
+    txt = open(os.path.join(ROOT, "include", "kspec.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return {k: int(v) for k, v in re.findall(r"\b(KSPEC_[A-Z0-9_]+)\s*=\s*(-?\d+)", txt)}
+
+
+def test_binding_constants_match_the_header_enums():
+    e = header_enums()
+    for name, v in _ffi.CUMU.items():
+        assert e["KSPEC_CUMU_" + name] == v
+    assert (e["KSPEC_IN_U8_IQ"], e["KSPEC_IN_C64"], e["KSPEC_IN_C128"]) == (_ffi.IN_U8_IQ, _ffi.IN_C64, _ffi.IN_C128)
+    for name, v in _ffi.PREC.items():
+        assert e["KSPEC_PREC_" + name.upper()] == v
+    for name, v in _ffi.COMPRESS.items():
+        assert e["KSPEC_COMPRESS_" + name] == v
+    for v, name in _ffi.PATH_NAME.items():
+        assert e["KSPEC_PATH_" + name.upper()] == v
+    assert (e["KSPEC_ROWS_NONE"], e["KSPEC_ROWS_LINEAR"], e["KSPEC_ROWS_DB"]) == (_ffi.ROWS_NONE, _ffi.ROWS_LINEAR, _ffi.ROWS_DB)
+
+
 def test_library_exports_every_symbol():
     assert os.path.isfile(_ffi.LIB_PATH), "build with __graft_entry__.build() / make -C prgs-sdr-kspecanal_b200"
     h = ctypes.CDLL(_ffi.LIB_PATH)
