@@ -20,7 +20,7 @@ namespace kspec {
 
 constexpr int MR_MAX_STAGES = 16;
 constexpr int MR_THREADS = 512;                   // default CTA (64 registers, two CTAs per SM); KSPEC_MR_THREADS=256 for tuning
-constexpr int MR_MAX_LINE = 6144;                 // longest line: one buffer pair of 2 x 96 KB
+constexpr int MR_MAX_LINE = 4096;                 // longest line: buffer pair 2 x 64 KB + at most 32 KB of twiddles always fits one CTA
 constexpr int MR_SMEM_BIG = 220 * 1024;           // one CTA per SM: long lines
 constexpr int MR_SMEM_STD = 112 * 1024;           // default tile: two CTAs per SM, so one CTA's loads overlap the other's butterflies
 constexpr int MR_TW_LO_BITS = 10;                 // inter-pass twiddle W_F^t = hi[t >> 10] * lo[t & 1023]: both tables cache-resident
