@@ -1,0 +1,361 @@
+// curscan_r32.cuh — the headline kernel: fused hot path for fftSize 2048 in float32 on large batches.
+//
+// Same job as curscan_smem_kernel (curscan_smem.cuh) — sdr_curscan K:385-397, data_cumu K:124-147, data_proc K:100-112,
+// zero_span stats K:471-476, _data_plotcompress K:168-202 for a whole batch of scans in one launch — with a transform
+// layout chosen for the pipe that bounds that kernel, the shared-memory data path (profiles/README.md):
+//
+//   2048 = 32 x 2 x 32.  A team of 64 threads (two warps) owns one frame, 32 complex points per thread.
+//     stage 0   thread j holds x[j + 64 m], m = 0..31 (ingest + window fused into the load): DFT32 over m in registers,
+//               then the boundary twiddle W_2048^(j k1) from a shared-memory table laid out [slot][thread].
+//     radix 2   the 64-point transform over j starts with the butterflies (j, j + 32).  The two threads sit 16 lanes
+//               apart in one warp and swap HALF of their values with shfl.xor: u = a + b, v = (a - b) W_64^j.
+//               The upper thread's stage-0 outputs are rotated by 16 slots (its window carries the sign (-1)^m), so both
+//               threads send slots 16..31 and keep 0..15: no lane-dependent register selection anywhere.
+//     exchange  ONE pass through shared memory (the 16/16/8 layout needs two): row rho = k1 + 32 c, column j mod 32.
+//     stage 1   thread rho: DFT32 over the row -> bins rho + 64 kappa, kappa = 0..31, i.e. the same "thread t owns
+//               bins t + NT m" convention as the other kernels, so |X|, cumulate and the per-scan epilogue are shared.
+//
+//   Per frame and SM this is ~576 shared-memory wavefronts (stage read 128, twiddles 128, shuffles 64, exchange 256)
+//   instead of ~890, one team barrier pair over two warps instead of two over four, and the same ~85 k FP32 lane
+//   operations.  Six teams (384 threads, <= 168 registers) share one SM; each team walks scans slot, slot + G, ...
+//   tools/r32_model.py is the index-level numpy model of this data flow (checked against numpy.fft).
+#pragma once
+#include "curscan_smem.cuh"
+
+namespace kspec {
+
+struct R32Cfg {
+    static constexpr int F = 2048, LOG2F = 11, P = 32, NT = 64, TEAMS = 6, CTA = NT * TEAMS;
+    static constexpr int PITCH = 33;                               // exchange row pitch (complex): conflict-free 64-bit column reads
+    static constexpr int EX_BYTES = 64 * PITCH * 8;                // one exchange buffer per team (16 896 B)
+    static constexpr int TW_BYTES = P * NT * 8;                    // boundary twiddles [slot][thread]
+};
+
+template <int INFMT> struct R32Stage {
+    static constexpr int EB = Ingest<float, INFMT>::ELEM_BYTES;
+    static constexpr int SLACK = EB >= 16 ? 0 : 16 / EB;
+    static constexpr int STAGE_BYTES = ((R32Cfg::F + SLACK) * EB + 127) / 128 * 128;
+    static constexpr int TEAM_BYTES = R32Cfg::EX_BYTES + STAGE_BYTES;
+    static constexpr int TW_OFS = R32Cfg::TEAMS * TEAM_BYTES;
+    static constexpr int SMEM_BYTES = TW_OFS + R32Cfg::TW_BYTES;
+    static constexpr bool OK = SMEM_BYTES <= 227 * 1024;
+};
+
+// exp(-2 pi i n / 32)
+__device__ __forceinline__ constexpr double root32_re(int n) {
+    constexpr double c[9] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708, 0.70710678118654752440,
+                             0.55557023301960222474, 0.38268343236508977173, 0.19509032201612826785, 0.0};
+    n &= 31;
+    return n <= 8 ? c[n] : (n <= 16 ? -c[16 - n] : (n <= 24 ? -c[n - 16] : c[32 - n]));
+}
+__device__ __forceinline__ constexpr double root32_im(int n) { return -root32_re((n + 24) & 31); }   // -sin(x) = -cos(x - pi/2)
+
+// 32-point forward DFT, natural order in and out: 4 x DFT8 over n1 (n = 4 n1 + n2), twiddles W_32^(n2 k1), 8 x DFT4 over n2
+__device__ __forceinline__ void dft32(float2 (&x)[32]) {
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2) {
+        float2 y[8];
+#pragma unroll
+        for (int n1 = 0; n1 < 8; ++n1) y[n1] = x[4 * n1 + n2];
+        dft8<float>(y);
+#pragma unroll
+        for (int k1 = 0; k1 < 8; ++k1) x[4 * k1 + n2] = y[k1];
+    }
+#pragma unroll
+    for (int k1 = 1; k1 < 8; ++k1)
+#pragma unroll
+        for (int n2 = 1; n2 < 4; ++n2) {
+            const int q = n2 * k1;
+            if (q == 8) x[4 * k1 + n2] = mul_mi(x[4 * k1 + n2]);
+            else x[4 * k1 + n2] = cmul(x[4 * k1 + n2], make_float2((float)root32_re(q), (float)root32_im(q)));
+        }
+    float2 o[32];
+#pragma unroll
+    for (int k1 = 0; k1 < 8; ++k1) {
+        dft4<float>(x[4 * k1], x[4 * k1 + 1], x[4 * k1 + 2], x[4 * k1 + 3]);
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) o[k1 + 8 * k2] = x[4 * k1 + k2];
+    }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) x[k] = o[k];
+}
+
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_1d_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ float ld_hint(const float* p, uint64_t pol) {
+    float v;
+    asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_hint(float* p, float v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+
+// float max / min as integer reductions (no return value, no load latency): non-negative floats order like signed integers,
+// negative ones like unsigned integers in reverse.  The slot must already hold a float (initialised by a plain store).
+__device__ __forceinline__ void red_max_f32(float* p, float v, uint64_t pol) {
+    if (v >= 0.0f) asm volatile("red.global.max.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(p), "r"(__float_as_int(v)), "l"(pol) : "memory");
+    else asm volatile("red.global.min.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(__float_as_uint(v)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void red_min_f32(float* p, float v, uint64_t pol) {
+    if (v >= 0.0f) asm volatile("red.global.min.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(p), "r"(__float_as_int(v)), "l"(pol) : "memory");
+    else asm volatile("red.global.max.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(__float_as_uint(v)), "l"(pol) : "memory");
+}
+
+// per-scan outputs from the normalised, fftshift-ed linear row in shared memory (erow[F]); thread tid handles the
+// positions tid + NT i.  Leaves dB - adj in erow for the waterfall compress.  data_proc K:100-112, zero_span K:469-478.
+template <int NT>
+__device__ __forceinline__ void scan_epilogue_rows(const ScanParams& p, float* erow, int64_t scan, bool valid, int64_t it, int slot, int tid,
+                                                uint64_t polKeep) {
+    constexpr int F = R32Cfg::F;
+    float* __restrict__ rows = reinterpret_cast<float*>(p.rows);
+    const bool needDb = (p.rowsKind == KSPEC_ROWS_DB) || p.wantStats || (p.hm != nullptr);
+    const bool needRow = (p.hm != nullptr);
+    float* __restrict__ wmax = reinterpret_cast<float*>(p.wsMax) + (int64_t)slot * F;
+    float* __restrict__ wmin = reinterpret_cast<float*>(p.wsMin) + (int64_t)slot * F;
+    const float gain = (float)p.gain, minAmp = (float)p.minAmp;
+    const float* __restrict__ adj = reinterpret_cast<const float*>(p.adj);
+    const int64_t ar = scan - (p.nScans - p.avgWin);
+    float* __restrict__ avgRow = (valid && ar >= 0) ? reinterpret_cast<float*>(p.avgRows) + ar * F : nullptr;
+#pragma unroll 4
+    for (int jj = tid; jj < F; jj += NT) {
+        float lin = erow[jj];
+        if (valid && p.rowsKind == KSPEC_ROWS_LINEAR) rows[scan * F + jj] = lin;
+        if (needDb) {
+            if (p.dbClip) lin = fmaxf(lin, minAmp);
+            float db = to_db(lin) - gain;
+            if (p.infToZero && isinf(db)) db = 0.0f;
+            if (valid && p.rowsKind == KSPEC_ROWS_DB) rows[scan * F + jj] = db;
+            if (p.wantStats) {
+                if (it == 0) {
+                    st_hint(&wmax[jj], valid ? db : -pos_inf<float>(), polKeep);
+                    st_hint(&wmin[jj], valid ? db : pos_inf<float>(), polKeep);
+                } else if (valid) {
+                    red_max_f32(&wmax[jj], db, polKeep);
+                    red_min_f32(&wmin[jj], db, polKeep);
+                }
+                if (avgRow) avgRow[jj] = db;
+            }
+            if (needRow) erow[jj] = adj ? db - adj[jj] : db;
+        }
+    }
+}
+
+template <int INFMT>
+__global__ void __launch_bounds__(R32Cfg::CTA, 1) curscan_r32_kernel(const ScanParams p) {
+    using C = R32Cfg;
+    using SC = R32Stage<INFMT>;
+    using IN = Ingest<float, INFMT>;
+    constexpr int P = C::P, F = C::F, NT = C::NT, TEAMS = C::TEAMS, PITCH = C::PITCH;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t mbar_all[TEAMS];
+    const int team = threadIdx.x / NT;
+    const int tid = threadIdx.x % NT;                              // = rho in stage 1: owns bins tid + 64 kappa
+    const int lane = tid & 31;
+    const int upper = lane >> 4;                                   // partner = lane ^ 16
+    const int jp = (lane & 15) + 16 * (tid >> 5);                  // j mod 32
+    const int j = jp + 32 * upper;                                 // stage 0: owns x[j + 64 m]
+    float2* ex = reinterpret_cast<float2*>(smem_raw + team * SC::TEAM_BYTES);
+    unsigned char* stage = smem_raw + team * SC::TEAM_BYTES + C::EX_BYTES;
+    float2* stw = reinterpret_cast<float2*>(smem_raw + SC::TW_OFS);
+    uint64_t* mbar = &mbar_all[team];
+    const bool leader = tid == 0;
+    auto sync = [team] { asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(NT) : "memory"); };
+
+    const float* __restrict__ gwin = reinterpret_cast<const float*>(p.win);
+    const float2* __restrict__ gtw = reinterpret_cast<const float2*>(p.tw);      // exp(-2 pi i k / 2048)
+    // boundary twiddles: slot s of thread t holds k1 = (s + 16 upper) mod 32 after stage 0
+    for (int i = threadIdx.x; i < P * NT; i += C::CTA) {
+        const int s = i / NT, t = i % NT;
+        const int up = (t & 31) >> 4, jj = (t & 15) + 16 * (t >> 5) + 32 * up;
+        stw[i] = gtw[(jj * ((s + 16 * up) & 31)) & (F - 1)];
+    }
+    // window in registers; the upper threads carry (-1)^m: their DFT32 outputs come out rotated by 16 slots
+    float win[P];
+#pragma unroll
+    for (int m = 0; m < P; ++m) {
+        const float w = gwin[j + NT * m];
+        win[m] = (upper && (m & 1)) ? -w : w;
+    }
+    float2 omega = gtw[32 * jp];                                   // W_64^(j mod 32); the upper thread computes b - a
+    if (upper) omega = make_float2(-omega.x, -omega.y);
+
+    const float u8off = (float)p.u8Offset, u8scale = (float)p.u8Scale;
+    const bool avgScaled = p.cumuMode == KSPEC_CUMU_AVG && p.nFrames <= 96;       // see curscan_smem.cuh
+    const float linScale = avgScaled ? (float)ldexp(p.linScale, -(p.nFrames - 1)) : (float)p.linScale;
+    const int slot = blockIdx.x * TEAMS + team;
+    const int64_t scansPerIter = (int64_t)gridDim.x * TEAMS;
+    const int64_t iters = (p.nScans + scansPerIter - 1) / scansPerIter;
+    const int64_t totalFrames = iters * p.nFrames;
+    const uint64_t polStream = l2_policy_evict_first();            // samples stream through L2 once (plus the overlap re-read)
+    const uint64_t polKeep = l2_policy_evict_last();               // the per-team Max/Min partials stay L2 resident
+
+    auto issue = [&](int64_t g) {                                  // leader only: fetch frame g (see curscan_smem.cuh)
+        const int64_t it = g / p.nFrames;
+        const int f = (int)(g - it * p.nFrames);
+        int64_t sc = it * scansPerIter + slot;
+        if (sc >= p.nScans) sc = p.nScans - 1;
+        const int64_t e0 = sc * p.scanStride + p.frameOffs[f];
+        constexpr int64_t GM = SC::SLACK > 0 ? SC::SLACK - 1 : 0;
+        const int64_t e0a = e0 & ~GM;
+        int64_t e1a = (e0 + F + GM) & ~GM;
+        const int64_t total = (p.nScans * p.scanStride + GM) & ~GM;
+        if (e1a > total) e1a = total;
+        const uint32_t bytes = (uint32_t)((e1a - e0a) * SC::EB);
+        mbar_expect_tx(mbar, bytes);
+        tma_load_1d_hint(stage, reinterpret_cast<const unsigned char*>(p.samples) + e0a * SC::EB, bytes, mbar, polStream);
+    };
+    if (leader) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (leader && totalFrames > 0) issue(0);
+
+    int64_t g = 0;
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t scan = it * scansPerIter + slot;
+        const bool valid = scan < p.nScans;
+        const int64_t scanC = valid ? scan : p.nScans - 1;
+        const int64_t sbase = scanC * p.scanStride;
+
+        float acc[P];
+        float avgW = 1.0f;
+        for (int f = 0; f < p.nFrames; ++f, ++g) {
+            float2 b[P];
+            {
+                mbar_wait(mbar, (uint32_t)(g & 1));
+                const int64_t fbase = sbase + p.frameOffs[f];
+                const typename IN::raw_t* sp = reinterpret_cast<const typename IN::raw_t*>(stage) + (SC::SLACK > 0 ? (int)(fbase & (SC::SLACK - 1)) : 0) + j;
+#pragma unroll
+                for (int m = 0; m < P; ++m) b[m] = IN::conv(sp[NT * m], win[m], u8off, u8scale);
+            }
+            dft32(b);
+            {
+                const float2* tw = stw + tid;
+#pragma unroll
+                for (int s = 0; s < P; ++s) b[s] = cmul(b[s], tw[s * NT]);
+            }
+            // radix-2 butterflies with the thread 16 lanes away: send slots 16..31, keep 0..15
+#pragma unroll
+            for (int s = 0; s < 16; ++s) {
+                float2 r;
+                r.x = __shfl_xor_sync(0xffffffffu, b[16 + s].x, 16);
+                r.y = __shfl_xor_sync(0xffffffffu, b[16 + s].y, 16);
+                const float2 a = b[s];
+                b[s] = a + r;                                      // u: row k1 = s + 16 upper
+                b[16 + s] = cmul(a - r, omega);                    // v: row k1 + 32
+            }
+            // every thread of the team is past its stage reads and past the previous frame's exchange reads
+            sync();
+            if (leader && g + 1 < totalFrames) issue(g + 1);
+            {
+                float2* q = ex + (16 * upper) * PITCH + jp;
+#pragma unroll
+                for (int s = 0; s < 16; ++s) {
+                    q[s * PITCH] = b[s];
+                    q[(s + 32) * PITCH] = b[16 + s];
+                }
+            }
+            sync();
+            {
+                const float2* q = ex + tid * PITCH;
+#pragma unroll
+                for (int i = 0; i < P; ++i) b[i] = q[i];
+            }
+            dft32(b);
+            // |X| in the same basic block as the transform's last layer (the square roots overlap the butterflies), then
+            // cumulate over the frames of this scan (data_cumu, K:124-147); normalisation once per scan
+            float mag[P];
+#pragma unroll
+            for (int m = 0; m < P; ++m) mag[m] = kabs(b[m]);
+            if (f == 0 || p.cumuMode == KSPEC_CUMU_RAW) {
+#pragma unroll
+                for (int m = 0; m < P; ++m) acc[m] = mag[m];
+            } else if (avgScaled) {
+#pragma unroll
+                for (int m = 0; m < P; ++m) acc[m] = fmaf(mag[m], avgW, acc[m]);
+                avgW += avgW;
+            } else if (p.cumuMode == KSPEC_CUMU_AVG) {
+#pragma unroll
+                for (int m = 0; m < P; ++m) acc[m] = (acc[m] + mag[m]) * 0.5f;
+            } else if (p.cumuMode == KSPEC_CUMU_MAX) {
+#pragma unroll
+                for (int m = 0; m < P; ++m) acc[m] = fmaxf(acc[m], mag[m]);
+            } else {
+#pragma unroll
+                for (int m = 0; m < P; ++m) acc[m] = fminf(acc[m], mag[m]);
+            }
+        }
+
+        // ---------------- per-scan epilogue ---------------------------------------------------------------------------------
+        // The normalised row goes through shared memory in fftshift-ed order (bin k -> position k ^ F/2) and a rolled loop
+        // walks the positions tid + 64 i: compact code (the frame loop stays resident in the instruction cache) and
+        // coalesced global accesses.  The running Max/Min of this team (K:471-474) are fire-and-forget reductions in L2.
+        float* erow = reinterpret_cast<float*>(ex);
+        sync();                                                    // the last frame's exchange reads are done
+#pragma unroll
+        for (int m = 0; m < P; ++m) erow[(tid + NT * m) ^ (F >> 1)] = acc[m] * linScale;
+        sync();
+        scan_epilogue_rows<NT>(p, erow, scan, valid, it, slot, tid, polKeep);
+        if (p.hm != nullptr) {
+            sync();
+            // _data_plotcompress (K:184-200): W groups of adjacent bins
+            const int W = p.hmW, gsz = F / W;
+            float* __restrict__ hm = reinterpret_cast<float*>(p.hm);
+            for (int w = tid; w < W; w += NT) {
+                float r = erow[w * gsz];
+                if (p.hmMode == KSPEC_COMPRESS_MAX) {
+                    for (int q = 1; q < gsz; ++q) r = fmaxf(r, erow[w * gsz + q]);
+                } else if (p.hmMode == KSPEC_COMPRESS_MIN) {
+                    for (int q = 1; q < gsz; ++q) r = fminf(r, erow[w * gsz + q]);
+                } else if (p.hmMode == KSPEC_COMPRESS_AVG) {
+                    for (int q = 1; q < gsz; ++q) r += erow[w * gsz + q];
+                    r /= (float)gsz;
+                }
+                if (valid) hm[scan * W + w] = r;
+            }
+            // the next frame's exchange writes come after that frame's first team barrier: no barrier needed here
+        }
+    }
+}
+
+template <int INFMT>
+static int launch_r32(const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info) {
+    using SC = R32Stage<INFMT>;
+    if constexpr (!SC::OK) {
+        return (int)cudaErrorInvalidValue;
+    } else {
+        auto k = curscan_r32_kernel<INFMT>;
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SC::SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        if (info) {
+            info->ctaThreads = R32Cfg::CTA;
+            info->smemBytes = SC::SMEM_BYTES;
+            info->teams = R32Cfg::TEAMS;
+            info->stages = 1;
+            int nb = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, R32Cfg::CTA, SC::SMEM_BYTES);
+            info->ctasPerSm = nb;
+            return 0;
+        }
+        k<<<grid, R32Cfg::CTA, SC::SMEM_BYTES, st>>>(p);
+        return (int)cudaGetLastError();
+    }
+}
+
+}  // namespace kspec

@@ -69,6 +69,8 @@ struct kspec_plan {
     int smReserve = 0;
     SmemKernelInfo ki{};          // base variant of the fused kernel
     SmemKernelInfo kiMulti{};     // multi-team variant (ctasPerSm == 0: not available for this shape)
+    SmemKernelInfo kiR32{};       // 32 x 2 x 32 layout (fftSize 2048, float32, uint8 / complex64 ingest)
+    bool r32Off = false;          // KSPEC_NO_R32=1 at plan creation: keep the 16/16/8 layouts (A/B runs, tests)
     int64_t convSize = 0;
     BigFft* big = nullptr;
     MixedRadix* mixed = nullptr;
@@ -189,9 +191,10 @@ int run_engine(kspec_plan* pl, ScanParams& p, int* slotsOut) {
                 return KSPEC_OK;
             }
         }
-        // large batches of the headline shape run four independent teams per CTA (one CTA per SM); small ones the base layout
-        const bool multi = pl->kiMulti.ctasPerSm > 0 && p.nScans >= (int64_t)2 * pl->smCount * pl->kiMulti.teams;
-        const SmemKernelInfo& ki = multi ? pl->kiMulti : pl->ki;
+        // large batches of the headline shape run several independent teams per CTA (one CTA per SM); small ones the base layout
+        const bool r32 = pl->kiR32.ctasPerSm > 0 && !pl->r32Off && p.nScans >= (int64_t)2 * pl->smCount * pl->kiR32.teams;
+        const bool multi = !r32 && pl->kiMulti.ctasPerSm > 0 && p.nScans >= (int64_t)2 * pl->smCount * pl->kiMulti.teams;
+        const SmemKernelInfo& ki = r32 ? pl->kiR32 : (multi ? pl->kiMulti : pl->ki);
         const int variant = multi ? SMEM_VARIANT_MULTI : SMEM_VARIANT_BASE;
         const int teams = ki.teams;
         int64_t need = (p.nScans + teams - 1) / teams;
@@ -210,7 +213,8 @@ int run_engine(kspec_plan* pl, ScanParams& p, int* slotsOut) {
         }
         const int ks = (int)(pl->kcount % kspec_plan::KT);
         cudaEventRecord(pl->kev[ks][0], pl->st);
-        int e = launch_smem(pl, variant, p, grid, nullptr);
+        int e = r32 ? (pl->inFmt == KSPEC_IN_U8_IQ ? launch_r32_u8(p, grid, pl->st, nullptr) : launch_r32_c64(p, grid, pl->st, nullptr))
+                    : launch_smem(pl, variant, p, grid, nullptr);
         cudaEventRecord(pl->kev[ks][1], pl->st);
         pl->kcount += 1;
         if (e != 0) { set_error("scan kernel launch failed: %s", cudaGetErrorString((cudaError_t)e)); return KSPEC_ERR_CUDA; }
@@ -426,6 +430,12 @@ int kspec_plan_create(kspec_plan** out, int fftSize, int64_t fullSize, double no
         if (launch_smem(pl, SMEM_VARIANT_MULTI, dummy, 0, &pl->kiMulti) != 0) { cudaGetLastError(); pl->kiMulti = SmemKernelInfo{}; }
         if (launch_smem(pl, SMEM_VARIANT_BASE, dummy, 0, &pl->ki) != 0) { set_error("kernel attribute query failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(KSPEC_ERR_CUDA); }
         if (pl->ki.ctasPerSm < 1) { set_error("fused kernel for fftSize %d does not fit on this device", fftSize); return fail(KSPEC_ERR_UNSUPPORTED); }
+        if (precision == KSPEC_PREC_F32 && pl->log2F == 11 && inFmt != KSPEC_IN_C128) {
+            const int e = inFmt == KSPEC_IN_U8_IQ ? launch_r32_u8(dummy, 0, pl->st, &pl->kiR32) : launch_r32_c64(dummy, 0, pl->st, &pl->kiR32);
+            if (e != 0) { cudaGetLastError(); pl->kiR32 = SmemKernelInfo{}; }
+            const char* no = getenv("KSPEC_NO_R32");
+            pl->r32Off = no && no[0] == '1';
+        }
     } else if (pl->path == KSPEC_PATH_MIXEDRADIX) {
         char err[256] = "";
         pl->mixed = mixedradix_create(precision, inFmt, fftSize, window, u8_offset, u8_scale, pl->st, err, sizeof(err));
@@ -474,7 +484,7 @@ int kspec_plan_info(const kspec_plan* pl, kspec_plan_info_t* info) {
     memset(info, 0, sizeof(*info));
     info->fft_size = pl->F; info->full_size = pl->S; info->n_frames = (int)pl->offs.size(); info->precision = pl->prec;
     info->path = pl->path; info->in_fmt = pl->inFmt; info->device = pl->device; info->sm_count = pl->smCount;
-    const SmemKernelInfo& ki = pl->kiMulti.ctasPerSm > 0 ? pl->kiMulti : pl->ki;     // what a large batch runs
+    const SmemKernelInfo& ki = (pl->kiR32.ctasPerSm > 0 && !pl->r32Off) ? pl->kiR32 : (pl->kiMulti.ctasPerSm > 0 ? pl->kiMulti : pl->ki);     // what a large batch runs
     info->cta_threads = ki.ctaThreads; info->ctas_per_sm = ki.ctasPerSm; info->smem_bytes = ki.smemBytes;
     info->scans_per_cta = ki.teams; info->tma_stages = ki.stages; info->conv_size = pl->convSize; info->win_adj = pl->winAdj;
     return KSPEC_OK;

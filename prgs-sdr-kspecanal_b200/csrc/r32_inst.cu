@@ -1,0 +1,7 @@
+// fused scan kernel for fftSize 2048 in float32, 32 x 2 x 32 layout (see curscan_r32.cuh): uint8 I/Q and complex64 ingest
+#include "curscan_r32.cuh"
+
+namespace kspec {
+int launch_r32_u8(const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info) { return launch_r32<KSPEC_IN_U8_IQ>(p, grid, st, info); }
+int launch_r32_c64(const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info) { return launch_r32<KSPEC_IN_C64>(p, grid, st, info); }
+}  // namespace kspec

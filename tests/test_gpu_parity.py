@@ -270,8 +270,9 @@ def test_large_batch_layout_ragged(fmt):
         first = plan.zerospan_batch(raw[:40 * per], 40, gain, xres, "MAX")                       # small batch: base layout
         got = plan.zerospan_batch(raw[40 * per:], n - 40, gain, xres, "MAX", rows="db",
                                   state=(first["max"], first["min"], first["avg"]))              # large batch: four teams per CTA
+        # plan.info describes what the largest batches run: the 32 x 2 x 32 layout (uint8 / complex64 ingest) or four teams
         if fmt != "c128":
-            assert plan.info.cta_threads == 512 and plan.info.scans_per_cta == 4
+            assert plan.info.cta_threads == 384 and plan.info.scans_per_cta == 6
     lin = [O.curscan(xin[k * S:(k + 1) * S], F, r, win) for k in range(n)]
     ref = O.zerospan(lin, gain, xres, "MAX")
     assert np.max(np.abs(got["rows"] - ref["cur_rows"][40:])) < DB_TOL
@@ -279,6 +280,53 @@ def test_large_batch_layout_ragged(fmt):
     assert np.max(np.abs(got["hm_rows"] - ref["hm_rows"][40:])) < DB_TOL
     for k in ("max", "min", "avg"):
         assert np.max(np.abs(got[k] - ref[k])) < DB_TOL, k
+
+
+@pytest.mark.parametrize("fmt,cumu,r,wname", [
+    ("c64", "AVG", 0.5, "hanning"), ("u8", "AVG", 0.5, "hanning"), ("c64", "MAX", 0.25, "kaiser"), ("u8", "MIN", 0.5, "hamming"),
+    ("c64", "RAW", 1.0, "ones"), ("c64", "AVG", 0.1, "hanning"), ("u8", "AVG", 0.1, "ones"),
+])
+def test_r32_layout_ragged(fmt, cumu, r, wname):
+    """fftSize 2048 float32 batches of >= 1776 scans run the 32 x 2 x 32 layout (curscan_r32.cuh: six 64-thread teams per SM,
+    one shared-memory exchange per frame): ragged scan count, carried state, every cumulate mode, even and odd frame offsets
+    (r = 0.1: 0, 204, 409, ...), both ingest formats; every output against the oracle."""
+    F, gain, xres = 2048, 19.1, 512
+    S = O.full_size(F, FS)
+    n = 6 * 148 * 2 + 41
+    win = O.window_table(wname, F)
+    x = synth.tones_noise(n * S, seed=31, dtype=np.complex128, gate=(300000, 0.5))
+    if fmt == "u8":
+        raw = synth.to_u8_iq(x)
+        xin = synth.from_u8_iq(raw)
+    else:
+        raw = x.astype(np.complex64)
+        xin = raw.astype(np.complex128)
+    per = 2 * S if fmt == "u8" else S
+    with Plan(F, S, r, win, cumu, _ffi.in_format(raw), precision="f32") as plan:
+        assert plan.info.cta_threads == 384 and plan.info.scans_per_cta == 6
+        first = plan.zerospan_batch(raw[:3 * per], 3, gain, xres, "MAX")                         # small batch: base layout
+        got = plan.zerospan_batch(raw[3 * per:], n - 3, gain, xres, "MAX", rows="db",
+                                  state=(first["max"], first["min"], first["avg"]))              # large batch: 32 x 2 x 32
+        lin = plan.zerospan_batch(raw[3 * per:], n - 3, gain, xres, "AVG", rows="linear")
+    ref_lin = [O.curscan(xin[k * S:(k + 1) * S], F, r, win, cumu) for k in range(n)]
+    ref = O.zerospan(ref_lin, gain, xres, "MAX")
+    rl = np.asarray(ref_lin[3:])
+    assert np.max(np.abs(lin["rows"] - rl)) < 3e-7 * rl.max()
+    if cumu == "MIN":
+        # the minimum over the frames leaves bins far below 1e-4 of the peak, where float32 cannot hold 1e-3 dB (F32_DYN):
+        # dB rows are compared on the bins above that floor, the statistics through the linear rows above
+        m = rl > F32_DYN * rl.max()
+        assert np.max(np.abs(got["rows"][m] - ref["cur_rows"][3:][m])) < DB_TOL
+        assert np.array_equal(np.argmax(got["rows"], axis=1), np.argmax(ref["cur_rows"][3:], axis=1))
+        assert np.max(np.abs(got["max"] - ref["max"])) < DB_TOL
+        return
+    assert np.max(np.abs(got["rows"] - ref["cur_rows"][3:])) < DB_TOL
+    assert np.array_equal(np.argmax(got["rows"], axis=1), np.argmax(ref["cur_rows"][3:], axis=1))
+    assert np.max(np.abs(got["hm_rows"] - ref["hm_rows"][3:])) < DB_TOL
+    for k in ("max", "min", "avg"):
+        assert np.max(np.abs(got[k] - ref[k])) < DB_TOL, k
+    ref2 = O.zerospan(ref_lin[3:], gain, xres, "AVG")
+    assert np.max(np.abs(lin["hm_rows"] - ref2["hm_rows"])) < DB_TOL
 
 
 def test_cfg2_full_size_quickfullscan():
