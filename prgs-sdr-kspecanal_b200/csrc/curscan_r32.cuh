@@ -26,9 +26,10 @@ namespace kspec {
 
 struct R32Cfg {
     static constexpr int F = 2048, LOG2F = 11, P = 32, NT = 64, TEAMS = 6, CTA = NT * TEAMS;
-    static constexpr int PITCH = 33;                               // exchange row pitch (complex): conflict-free 64-bit column reads
-    static constexpr int EX_BYTES = 64 * PITCH * 8;                // one exchange buffer per team (16 896 B)
-    static constexpr int TW_BYTES = P * NT * 8;                    // boundary twiddles [slot][thread]
+    static constexpr int PITCH = 34;                               // exchange row pitch (complex): conflict-free 128-bit row reads
+    static constexpr int EX_BYTES = 64 * PITCH * 8;                // one exchange buffer per team (17 408 B)
+    static constexpr int TW_BYTES = P * NT * 8;                    // boundary twiddles [slot pair][thread][2]
+    static constexpr int MAX_FRAMES = 1024;                        // frame offsets of a scan are kept in shared memory
 };
 
 template <int INFMT> struct R32Stage {
@@ -50,14 +51,47 @@ __device__ __forceinline__ constexpr double root32_re(int n) {
 }
 __device__ __forceinline__ constexpr double root32_im(int n) { return -root32_re((n + 24) & 31); }   // -sin(x) = -cos(x - pi/2)
 
-// 32-point forward DFT, natural order in and out: 4 x DFT8 over n1 (n = 4 n1 + n2), twiddles W_32^(n2 k1), 8 x DFT4 over n2
-__device__ __forceinline__ void dft32(float2 (&x)[32]) {
+// DFT8 of x[i] * w[i]: the window multiply is folded into the first butterfly layer (a*wa +- b*wb = one multiply and two
+// fused multiply-adds instead of two multiplies and two adds)
+__device__ __forceinline__ void dft8_win(float2 (&x)[8], const float (&w)[8]) {
+    const float h = 0.70710678118654752440f;
+    float2 s[4], d[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 t = cscale(x[i + 4], w[i + 4]);
+        const float2 wi = make_float2(w[i], w[i]);
+        s[i] = __ffma2_rn(x[i], wi, t);
+        d[i] = __ffma2_rn(x[i], wi, make_float2(-t.x, -t.y));
+    }
+    // evens: dft4(x0, x2, x4, x6);  odds: dft4(x1, x3, x5, x7)   (first layer done: s = a + b, d = a - b)
+    float2 e0 = s[0] + s[2], e2 = s[0] - s[2], e1 = d[0] + mul_mi(d[2]), e3 = d[0] - mul_mi(d[2]);
+    float2 o0 = s[1] + s[3], q2 = s[1] - s[3], q1 = d[1] + mul_mi(d[3]), q3 = d[1] - mul_mi(d[3]);
+    const float2 o1 = cmul(q1, make_float2(h, -h));
+    const float2 o2 = mul_mi(q2);
+    const float2 o3 = cmul(q3, make_float2(-h, -h));
+    x[0] = e0 + o0; x[4] = e0 - o0;
+    x[1] = e1 + o1; x[5] = e1 - o1;
+    x[2] = e2 + o2; x[6] = e2 - o2;
+    x[3] = e3 + o3; x[7] = e3 - o3;
+}
+
+// 32-point forward DFT: 4 x DFT8 over n1 (n = 4 n1 + n2), twiddles W_32^(n2 k1), 8 x DFT4 over n2.
+// dft32_head does everything but the last layer; WIN: the inputs are multiplied by w[] on the way in.
+template <bool WIN>
+__device__ __forceinline__ void dft32_head(float2 (&x)[32], const float (&w)[32]) {
 #pragma unroll
     for (int n2 = 0; n2 < 4; ++n2) {
         float2 y[8];
 #pragma unroll
         for (int n1 = 0; n1 < 8; ++n1) y[n1] = x[4 * n1 + n2];
-        dft8<float>(y);
+        if constexpr (WIN) {
+            float wy[8];
+#pragma unroll
+            for (int n1 = 0; n1 < 8; ++n1) wy[n1] = w[4 * n1 + n2];
+            dft8_win(y, wy);
+        } else {
+            dft8<float>(y);
+        }
 #pragma unroll
         for (int k1 = 0; k1 < 8; ++k1) x[4 * k1 + n2] = y[k1];
     }
@@ -69,6 +103,11 @@ __device__ __forceinline__ void dft32(float2 (&x)[32]) {
             if (q == 8) x[4 * k1 + n2] = mul_mi(x[4 * k1 + n2]);
             else x[4 * k1 + n2] = cmul(x[4 * k1 + n2], make_float2((float)root32_re(q), (float)root32_im(q)));
         }
+}
+// natural order in and out
+__device__ __forceinline__ void dft32(float2 (&x)[32]) {
+    const float none[32] = {};
+    dft32_head<false>(x, none);
     float2 o[32];
 #pragma unroll
     for (int k1 = 0; k1 < 8; ++k1) {
@@ -78,6 +117,53 @@ __device__ __forceinline__ void dft32(float2 (&x)[32]) {
     }
 #pragma unroll
     for (int k = 0; k < 32; ++k) x[k] = o[k];
+}
+
+// Stage 0 of a frame for one thread: windowed DFT32 of its 32 samples, boundary twiddle W_2048^(j k1), the radix-2 butterflies
+// with the thread 16 lanes away (it sends its slots 16..31 and keeps 0..15) and the exchange writes, as ONE software pipeline
+// over the eight groups of the transform's last layer: group k1 finishes slots {k1, k1+8, k1+16, k1+24}, fetches their four
+// twiddles with two 128-bit loads, swaps (k1+16, k1+24) with the partner and stores u (row s + 16 upper) and v (row + 32).
+// The shared-memory and shuffle latencies of one group hide behind the arithmetic of the others.
+__device__ __forceinline__ void r32_stage0(float2 (&b)[32], const float (&win)[32], const float4* tw4, float2 omega, float2* exw) {
+    constexpr int NT = R32Cfg::NT, PITCH = R32Cfg::PITCH;
+    dft32_head<true>(b, win);
+#pragma unroll
+    for (int k1 = 0; k1 < 8; ++k1) {
+        dft4<float>(b[4 * k1], b[4 * k1 + 1], b[4 * k1 + 2], b[4 * k1 + 3]);     // -> slots k1 + 8 k2
+        const float4 tA = tw4[(2 * k1) * NT], tB = tw4[(2 * k1 + 1) * NT];
+        const float2 y0 = cmul(b[4 * k1], make_float2(tA.x, tA.y));               // slot k1
+        const float2 y1 = cmul(b[4 * k1 + 1], make_float2(tA.z, tA.w));           // slot k1 + 8
+        const float2 y2 = cmul(b[4 * k1 + 2], make_float2(tB.x, tB.y));           // slot k1 + 16
+        const float2 y3 = cmul(b[4 * k1 + 3], make_float2(tB.z, tB.w));           // slot k1 + 24
+        float2 r0, r1;
+        r0.x = __shfl_xor_sync(0xffffffffu, y2.x, 16);
+        r0.y = __shfl_xor_sync(0xffffffffu, y2.y, 16);
+        r1.x = __shfl_xor_sync(0xffffffffu, y3.x, 16);
+        r1.y = __shfl_xor_sync(0xffffffffu, y3.y, 16);
+        exw[k1 * PITCH] = y0 + r0;                                                // u, s = k1
+        exw[(k1 + 32) * PITCH] = cmul(y0 - r0, omega);                            // v
+        exw[(k1 + 8) * PITCH] = y1 + r1;                                          // u, s = k1 + 8
+        exw[(k1 + 40) * PITCH] = cmul(y1 - r1, omega);                            // v
+    }
+}
+
+// raw sample -> float2 without scale or window (both live in the window registers of the R32 kernels)
+template <int INFMT> struct R32Raw;
+template <> struct R32Raw<KSPEC_IN_U8_IQ> {
+    typedef uchar2 raw_t;
+    static __device__ __forceinline__ float2 get(uchar2 v, float off) { return make_float2((float)v.x - off, (float)v.y - off); }
+};
+template <> struct R32Raw<KSPEC_IN_C64> {
+    typedef float2 raw_t;
+    static __device__ __forceinline__ float2 get(float2 v, float) { return v; }
+};
+
+// |X| with one multiply and one fused multiply-add in front of the square root
+__device__ __forceinline__ float kabs_fma(float2 a) {
+    const float s = fmaf(a.y, a.y, a.x * a.x);
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s));
+    return r;
 }
 
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
@@ -154,15 +240,28 @@ __device__ __forceinline__ void scan_epilogue_rows(const ScanParams& p, float* e
     }
 }
 
+// boundary twiddles W_2048^(j k1) in shared memory: slot s of thread t holds k1 = (s + 16 upper) mod 32 after stage 0; the table
+// is laid out [2 (s & 7) + (s >> 4)][t][(s >> 3) & 1]: the slots {g, g+8} and {g+16, g+24} of a last-layer group are one
+// 128-bit load each
+__device__ __forceinline__ void r32_build_twiddles(float2* stw, const float2* __restrict__ gtw, int thread, int nthreads) {
+    constexpr int NT = R32Cfg::NT, P = R32Cfg::P, F = R32Cfg::F;
+    for (int i = thread; i < P * NT; i += nthreads) {
+        const int s = i / NT, t = i % NT;
+        const int up = (t & 31) >> 4, jj = (t & 15) + 16 * (t >> 5) + 32 * up;
+        stw[((2 * (s & 7) + (s >> 4)) * NT + t) * 2 + ((s >> 3) & 1)] = gtw[(jj * ((s + 16 * up) & 31)) & (F - 1)];
+    }
+}
+
 template <int INFMT>
 __global__ void __launch_bounds__(R32Cfg::CTA, 1) curscan_r32_kernel(const ScanParams p) {
     using C = R32Cfg;
     using SC = R32Stage<INFMT>;
-    using IN = Ingest<float, INFMT>;
+    using IN = R32Raw<INFMT>;
     constexpr int P = C::P, F = C::F, NT = C::NT, TEAMS = C::TEAMS, PITCH = C::PITCH;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t mbar_all[TEAMS];
+    __shared__ int32_t foffs[C::MAX_FRAMES];                       // K:386 frame starts inside a scan
     const int team = threadIdx.x / NT;
     const int tid = threadIdx.x % NT;                              // = rho in stage 1: owns bins tid + 64 kappa
     const int lane = tid & 31;
@@ -179,22 +278,21 @@ __global__ void __launch_bounds__(R32Cfg::CTA, 1) curscan_r32_kernel(const ScanP
     const float* __restrict__ gwin = reinterpret_cast<const float*>(p.win);
     const float2* __restrict__ gtw = reinterpret_cast<const float2*>(p.tw);      // exp(-2 pi i k / 2048)
     // boundary twiddles: slot s of thread t holds k1 = (s + 16 upper) mod 32 after stage 0
-    for (int i = threadIdx.x; i < P * NT; i += C::CTA) {
-        const int s = i / NT, t = i % NT;
-        const int up = (t & 31) >> 4, jj = (t & 15) + 16 * (t >> 5) + 32 * up;
-        stw[i] = gtw[(jj * ((s + 16 * up) & 31)) & (F - 1)];
-    }
-    // window in registers; the upper threads carry (-1)^m: their DFT32 outputs come out rotated by 16 slots
+    r32_build_twiddles(stw, gtw, threadIdx.x, C::CTA);
+    for (int i = threadIdx.x; i < p.nFrames; i += C::CTA) foffs[i] = p.frameOffs[i];
+    // window in registers (the uint8 scale rides in it); the upper threads carry (-1)^m: their DFT32 outputs come out rotated
+    // by 16 slots
+    const float u8off = (float)p.u8Offset;
+    const float wscale = INFMT == KSPEC_IN_U8_IQ ? (float)p.u8Scale : 1.0f;
     float win[P];
 #pragma unroll
     for (int m = 0; m < P; ++m) {
         const float w = gwin[j + NT * m];
-        win[m] = (upper && (m & 1)) ? -w : w;
+        win[m] = ((upper && (m & 1)) ? -w : w) * wscale;
     }
     float2 omega = gtw[32 * jp];                                   // W_64^(j mod 32); the upper thread computes b - a
     if (upper) omega = make_float2(-omega.x, -omega.y);
 
-    const float u8off = (float)p.u8Offset, u8scale = (float)p.u8Scale;
     const bool avgScaled = p.cumuMode == KSPEC_CUMU_AVG && p.nFrames <= 96;       // see curscan_smem.cuh
     const float linScale = avgScaled ? (float)ldexp(p.linScale, -(p.nFrames - 1)) : (float)p.linScale;
     const int slot = blockIdx.x * TEAMS + team;
@@ -204,16 +302,15 @@ __global__ void __launch_bounds__(R32Cfg::CTA, 1) curscan_r32_kernel(const ScanP
     const uint64_t polStream = l2_policy_evict_first();            // samples stream through L2 once (plus the overlap re-read)
     const uint64_t polKeep = l2_policy_evict_last();               // the per-team Max/Min partials stay L2 resident
 
-    auto issue = [&](int64_t g) {                                  // leader only: fetch frame g (see curscan_smem.cuh)
-        const int64_t it = g / p.nFrames;
-        const int f = (int)(g - it * p.nFrames);
-        int64_t sc = it * scansPerIter + slot;
-        if (sc >= p.nScans) sc = p.nScans - 1;
-        const int64_t e0 = sc * p.scanStride + p.frameOffs[f];
+    // leader only: fetch frame f of scan sc into the stage buffer.  A bulk copy covers the 16-byte granules around the
+    // frame (offsets can be odd) and is clipped at the end of the batch (see curscan_smem.cuh).
+    const int64_t totalElems = p.nScans * p.scanStride;
+    auto issue = [&](int64_t sc, int f) {
         constexpr int64_t GM = SC::SLACK > 0 ? SC::SLACK - 1 : 0;
+        const int64_t e0 = sc * p.scanStride + foffs[f];
         const int64_t e0a = e0 & ~GM;
         int64_t e1a = (e0 + F + GM) & ~GM;
-        const int64_t total = (p.nScans * p.scanStride + GM) & ~GM;
+        const int64_t total = (totalElems + GM) & ~GM;
         if (e1a > total) e1a = total;
         const uint32_t bytes = (uint32_t)((e1a - e0a) * SC::EB);
         mbar_expect_tx(mbar, bytes);
@@ -224,7 +321,7 @@ __global__ void __launch_bounds__(R32Cfg::CTA, 1) curscan_r32_kernel(const ScanP
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (leader && totalFrames > 0) issue(0);
+    if (leader && totalFrames > 0) issue(slot < p.nScans ? slot : p.nScans - 1, 0);
 
     int64_t g = 0;
     for (int64_t it = 0; it < iters; ++it) {
@@ -239,50 +336,36 @@ __global__ void __launch_bounds__(R32Cfg::CTA, 1) curscan_r32_kernel(const ScanP
             float2 b[P];
             {
                 mbar_wait(mbar, (uint32_t)(g & 1));
-                const int64_t fbase = sbase + p.frameOffs[f];
-                const typename IN::raw_t* sp = reinterpret_cast<const typename IN::raw_t*>(stage) + (SC::SLACK > 0 ? (int)(fbase & (SC::SLACK - 1)) : 0) + j;
+                const int mis = SC::SLACK > 0 ? (((int)sbase + foffs[f]) & (SC::SLACK - 1)) : 0;
+                const typename IN::raw_t* sp = reinterpret_cast<const typename IN::raw_t*>(stage) + mis + j;
 #pragma unroll
-                for (int m = 0; m < P; ++m) b[m] = IN::conv(sp[NT * m], win[m], u8off, u8scale);
+                for (int m = 0; m < P; ++m) b[m] = IN::get(sp[NT * m], u8off);
             }
-            dft32(b);
-            {
-                const float2* tw = stw + tid;
-#pragma unroll
-                for (int s = 0; s < P; ++s) b[s] = cmul(b[s], tw[s * NT]);
-            }
-            // radix-2 butterflies with the thread 16 lanes away: send slots 16..31, keep 0..15
-#pragma unroll
-            for (int s = 0; s < 16; ++s) {
-                float2 r;
-                r.x = __shfl_xor_sync(0xffffffffu, b[16 + s].x, 16);
-                r.y = __shfl_xor_sync(0xffffffffu, b[16 + s].y, 16);
-                const float2 a = b[s];
-                b[s] = a + r;                                      // u: row k1 = s + 16 upper
-                b[16 + s] = cmul(a - r, omega);                    // v: row k1 + 32
-            }
-            // every thread of the team is past its stage reads and past the previous frame's exchange reads
+            // every thread of the team is past its stage reads and (program order) past the previous frame's exchange reads
             sync();
-            if (leader && g + 1 < totalFrames) issue(g + 1);
+            if (leader && g + 1 < totalFrames) {
+                const bool lastF = f + 1 == p.nFrames;
+                int64_t sc = lastF ? scan + scansPerIter : scanC;
+                if (sc >= p.nScans) sc = p.nScans - 1;
+                issue(sc, lastF ? 0 : f + 1);
+            }
+            r32_stage0(b, win, reinterpret_cast<const float4*>(stw) + tid, omega, ex + (16 * upper) * PITCH + jp);
+            sync();
             {
-                float2* q = ex + (16 * upper) * PITCH + jp;
+                const float4* q4 = reinterpret_cast<const float4*>(ex + tid * PITCH);
 #pragma unroll
-                for (int s = 0; s < 16; ++s) {
-                    q[s * PITCH] = b[s];
-                    q[(s + 32) * PITCH] = b[16 + s];
+                for (int i = 0; i < P; i += 2) {
+                    const float4 v = q4[i >> 1];
+                    b[i] = make_float2(v.x, v.y);
+                    b[i + 1] = make_float2(v.z, v.w);
                 }
-            }
-            sync();
-            {
-                const float2* q = ex + tid * PITCH;
-#pragma unroll
-                for (int i = 0; i < P; ++i) b[i] = q[i];
             }
             dft32(b);
             // |X| in the same basic block as the transform's last layer (the square roots overlap the butterflies), then
             // cumulate over the frames of this scan (data_cumu, K:124-147); normalisation once per scan
             float mag[P];
 #pragma unroll
-            for (int m = 0; m < P; ++m) mag[m] = kabs(b[m]);
+            for (int m = 0; m < P; ++m) mag[m] = kabs_fma(b[m]);
             if (f == 0 || p.cumuMode == KSPEC_CUMU_RAW) {
 #pragma unroll
                 for (int m = 0; m < P; ++m) acc[m] = mag[m];

@@ -71,6 +71,7 @@ struct kspec_plan {
     SmemKernelInfo kiMulti{};     // multi-team variant (ctasPerSm == 0: not available for this shape)
     SmemKernelInfo kiR32{};       // 32 x 2 x 32 layout (fftSize 2048, float32, uint8 / complex64 ingest)
     bool r32Off = false;          // KSPEC_NO_R32=1 at plan creation: keep the 16/16/8 layouts (A/B runs, tests)
+    bool r32Pipe = false;         // kiR32 describes the two-role pipeline (curscan_r32p.cuh); KSPEC_R32_SERIAL=1 selects the one-role kernel
     int64_t convSize = 0;
     BigFft* big = nullptr;
     MixedRadix* mixed = nullptr;
@@ -192,7 +193,7 @@ int run_engine(kspec_plan* pl, ScanParams& p, int* slotsOut) {
             }
         }
         // large batches of the headline shape run several independent teams per CTA (one CTA per SM); small ones the base layout
-        const bool r32 = pl->kiR32.ctasPerSm > 0 && !pl->r32Off && p.nScans >= (int64_t)2 * pl->smCount * pl->kiR32.teams;
+        const bool r32 = pl->kiR32.ctasPerSm > 0 && !pl->r32Off && nFrames <= 1024 && p.nScans >= (int64_t)2 * pl->smCount * pl->kiR32.teams;
         const bool multi = !r32 && pl->kiMulti.ctasPerSm > 0 && p.nScans >= (int64_t)2 * pl->smCount * pl->kiMulti.teams;
         const SmemKernelInfo& ki = r32 ? pl->kiR32 : (multi ? pl->kiMulti : pl->ki);
         const int variant = multi ? SMEM_VARIANT_MULTI : SMEM_VARIANT_BASE;
@@ -213,8 +214,10 @@ int run_engine(kspec_plan* pl, ScanParams& p, int* slotsOut) {
         }
         const int ks = (int)(pl->kcount % kspec_plan::KT);
         cudaEventRecord(pl->kev[ks][0], pl->st);
-        int e = r32 ? (pl->inFmt == KSPEC_IN_U8_IQ ? launch_r32_u8(p, grid, pl->st, nullptr) : launch_r32_c64(p, grid, pl->st, nullptr))
-                    : launch_smem(pl, variant, p, grid, nullptr);
+        int e;
+        if (r32 && pl->r32Pipe) e = pl->inFmt == KSPEC_IN_U8_IQ ? launch_r32p_u8(p, grid, pl->st, nullptr) : launch_r32p_c64(p, grid, pl->st, nullptr);
+        else if (r32) e = pl->inFmt == KSPEC_IN_U8_IQ ? launch_r32_u8(p, grid, pl->st, nullptr) : launch_r32_c64(p, grid, pl->st, nullptr);
+        else e = launch_smem(pl, variant, p, grid, nullptr);
         cudaEventRecord(pl->kev[ks][1], pl->st);
         pl->kcount += 1;
         if (e != 0) { set_error("scan kernel launch failed: %s", cudaGetErrorString((cudaError_t)e)); return KSPEC_ERR_CUDA; }
@@ -431,10 +434,17 @@ int kspec_plan_create(kspec_plan** out, int fftSize, int64_t fullSize, double no
         if (launch_smem(pl, SMEM_VARIANT_BASE, dummy, 0, &pl->ki) != 0) { set_error("kernel attribute query failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(KSPEC_ERR_CUDA); }
         if (pl->ki.ctasPerSm < 1) { set_error("fused kernel for fftSize %d does not fit on this device", fftSize); return fail(KSPEC_ERR_UNSUPPORTED); }
         if (precision == KSPEC_PREC_F32 && pl->log2F == 11 && inFmt != KSPEC_IN_C128) {
-            const int e = inFmt == KSPEC_IN_U8_IQ ? launch_r32_u8(dummy, 0, pl->st, &pl->kiR32) : launch_r32_c64(dummy, 0, pl->st, &pl->kiR32);
-            if (e != 0) { cudaGetLastError(); pl->kiR32 = SmemKernelInfo{}; }
             const char* no = getenv("KSPEC_NO_R32");
+            const char* ser = getenv("KSPEC_R32_SERIAL");
             pl->r32Off = no && no[0] == '1';
+            pl->r32Pipe = !(ser && ser[0] == '1');
+            int e = pl->r32Pipe ? (inFmt == KSPEC_IN_U8_IQ ? launch_r32p_u8(dummy, 0, pl->st, &pl->kiR32) : launch_r32p_c64(dummy, 0, pl->st, &pl->kiR32)) : 1;
+            if (e != 0 || pl->kiR32.ctasPerSm < 1) {
+                cudaGetLastError();
+                pl->r32Pipe = false;
+                e = inFmt == KSPEC_IN_U8_IQ ? launch_r32_u8(dummy, 0, pl->st, &pl->kiR32) : launch_r32_c64(dummy, 0, pl->st, &pl->kiR32);
+                if (e != 0) { cudaGetLastError(); pl->kiR32 = SmemKernelInfo{}; }
+            }
         }
     } else if (pl->path == KSPEC_PATH_MIXEDRADIX) {
         char err[256] = "";

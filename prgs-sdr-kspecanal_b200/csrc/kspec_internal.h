@@ -60,6 +60,9 @@ constexpr int SMEM_VARIANT_BASE = 0, SMEM_VARIANT_MULTI = 1, SMEM_VARIANT_FRAMES
 // fftSize 2048, float32, large batches: the 32 x 2 x 32 layout with one shared-memory exchange per frame (curscan_r32.cuh)
 int launch_r32_u8(const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info);
 int launch_r32_c64(const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info);
+// ... and the same layout as a two-role pipeline: four teams of 2 + 2 warps (curscan_r32p.cuh)
+int launch_r32p_u8(const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info);
+int launch_r32p_c64(const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info);
 constexpr int SMEM_MAX_LOG2F_F32 = 14;
 constexpr int SMEM_MAX_LOG2F_F64 = 13;
 constexpr int SMEM_MIN_LOG2F = 4;
