@@ -190,22 +190,23 @@ __device__ __forceinline__ void st_hint(float* p, float v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
 }
 
-// float max / min as integer reductions (no return value, no load latency): non-negative floats order like signed integers,
-// negative ones like unsigned integers in reverse.  The slot must already hold a float (initialised by a plain store).
-__device__ __forceinline__ void red_max_f32(float* p, float v, uint64_t pol) {
-    if (v >= 0.0f) asm volatile("red.global.max.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(p), "r"(__float_as_int(v)), "l"(pol) : "memory");
-    else asm volatile("red.global.min.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(__float_as_uint(v)), "l"(pol) : "memory");
+// Max / Min of non-negative floats as integer reductions in L2 (no return value, hence no load latency): the normalised
+// amplitudes are >= 0, where float order is signed-integer order.  The slot is initialised by a plain store.
+__device__ __forceinline__ void red_max_pos(float* p, float v, uint64_t pol) {
+    asm volatile("red.global.max.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(p), "r"(__float_as_int(v)), "l"(pol) : "memory");
 }
-__device__ __forceinline__ void red_min_f32(float* p, float v, uint64_t pol) {
-    if (v >= 0.0f) asm volatile("red.global.min.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(p), "r"(__float_as_int(v)), "l"(pol) : "memory");
-    else asm volatile("red.global.max.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(__float_as_uint(v)), "l"(pol) : "memory");
+__device__ __forceinline__ void red_min_pos(float* p, float v, uint64_t pol) {
+    asm volatile("red.global.min.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(p), "r"(__float_as_int(v)), "l"(pol) : "memory");
 }
 
-// per-scan outputs from the normalised, fftshift-ed linear row in shared memory (erow[F]); thread tid handles the
-// positions tid + NT i.  Leaves dB - adj in erow for the waterfall compress.  data_proc K:100-112, zero_span K:469-478.
+// Per-scan outputs from the normalised, fftshift-ed linear row in shared memory (erow[F]).  data_proc K:100-112, zero_span
+// K:469-478, _data_plotcompress K:184-200.  The running Max/Min of this team (K:471-474) are kept as LINEAR amplitudes
+// (10 log10 is monotone; stats_finish_kernel converts them exactly as the rows are converted here).
+// Returns true when the waterfall row has been written as well (fast path), false when dB - adj is left in erow for the
+// caller's compress step.
 template <int NT>
-__device__ __forceinline__ void scan_epilogue_rows(const ScanParams& p, float* erow, int64_t scan, bool valid, int64_t it, int slot, int tid,
-                                                uint64_t polKeep) {
+__device__ __forceinline__ bool scan_epilogue_rows(const ScanParams& p, float* erow, int64_t scan, bool valid, int64_t it, int slot, int tid,
+                                                   uint64_t polKeep) {
     constexpr int F = R32Cfg::F;
     float* __restrict__ rows = reinterpret_cast<float*>(p.rows);
     const bool needDb = (p.rowsKind == KSPEC_ROWS_DB) || p.wantStats || (p.hm != nullptr);
@@ -215,7 +216,34 @@ __device__ __forceinline__ void scan_epilogue_rows(const ScanParams& p, float* e
     const float gain = (float)p.gain, minAmp = (float)p.minAmp;
     const float* __restrict__ adj = reinterpret_cast<const float*>(p.adj);
     const int64_t ar = scan - (p.nScans - p.avgWin);
-    float* __restrict__ avgRow = (valid && ar >= 0) ? reinterpret_cast<float*>(p.avgRows) + ar * F : nullptr;
+    float* __restrict__ avgRow = (valid && ar >= 0 && p.wantStats) ? reinterpret_cast<float*>(p.avgRows) + ar * F : nullptr;
+
+    // Fast path — the streaming case: no rows wanted, Max/Min partials, a MAX or MIN waterfall row of 4-bin groups, no
+    // baseline, no clip.  Max/Min and the group reduce work on the linear values (monotone map), so only one dB conversion per
+    // waterfall bin is left: 4 instructions per bin instead of ~40.
+    if (p.rowsKind == KSPEC_ROWS_NONE && p.wantStats && needRow && adj == nullptr && avgRow == nullptr && !p.dbClip && !p.infToZero &&
+        p.hmW * 4 == F && (p.hmMode == KSPEC_COMPRESS_MAX || p.hmMode == KSPEC_COMPRESS_MIN)) {
+        float* __restrict__ hm = reinterpret_cast<float*>(p.hm) + scan * p.hmW;
+        const bool useMax = p.hmMode == KSPEC_COMPRESS_MAX;
+#pragma unroll 2
+        for (int q = tid; q < F / 4; q += NT) {
+            const float4 v = reinterpret_cast<const float4*>(erow)[q];
+            float* mx = wmax + 4 * q;
+            float* mn = wmin + 4 * q;
+            if (it == 0) {
+                const float4 hi = valid ? v : make_float4(0.0f, 0.0f, 0.0f, 0.0f);            // idle team: identity of max over amplitudes
+                const float4 lo = valid ? v : make_float4(pos_inf<float>(), pos_inf<float>(), pos_inf<float>(), pos_inf<float>());
+                asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(mx), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w), "l"(polKeep) : "memory");
+                asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(mn), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w), "l"(polKeep) : "memory");
+            } else if (valid) {
+                red_max_pos(mx, v.x, polKeep); red_max_pos(mx + 1, v.y, polKeep); red_max_pos(mx + 2, v.z, polKeep); red_max_pos(mx + 3, v.w, polKeep);
+                red_min_pos(mn, v.x, polKeep); red_min_pos(mn + 1, v.y, polKeep); red_min_pos(mn + 2, v.z, polKeep); red_min_pos(mn + 3, v.w, polKeep);
+            }
+            const float g4 = useMax ? fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) : fminf(fminf(v.x, v.y), fminf(v.z, v.w));
+            if (valid) hm[q] = to_db(g4) - gain;
+        }
+        return true;
+    }
 #pragma unroll 4
     for (int jj = tid; jj < F; jj += NT) {
         float lin = erow[jj];
@@ -227,17 +255,18 @@ __device__ __forceinline__ void scan_epilogue_rows(const ScanParams& p, float* e
             if (valid && p.rowsKind == KSPEC_ROWS_DB) rows[scan * F + jj] = db;
             if (p.wantStats) {
                 if (it == 0) {
-                    st_hint(&wmax[jj], valid ? db : -pos_inf<float>(), polKeep);
-                    st_hint(&wmin[jj], valid ? db : pos_inf<float>(), polKeep);
+                    st_hint(&wmax[jj], valid ? lin : 0.0f, polKeep);
+                    st_hint(&wmin[jj], valid ? lin : pos_inf<float>(), polKeep);
                 } else if (valid) {
-                    red_max_f32(&wmax[jj], db, polKeep);
-                    red_min_f32(&wmin[jj], db, polKeep);
+                    red_max_pos(&wmax[jj], lin, polKeep);
+                    red_min_pos(&wmin[jj], lin, polKeep);
                 }
                 if (avgRow) avgRow[jj] = db;
             }
             if (needRow) erow[jj] = adj ? db - adj[jj] : db;
         }
     }
+    return false;
 }
 
 // boundary twiddles W_2048^(j k1) in shared memory: slot s of thread t holds k1 = (s + 16 upper) mod 32 after stage 0; the table
@@ -302,10 +331,22 @@ __global__ void __launch_bounds__(R32Cfg::CTA, 1) curscan_r32_kernel(const ScanP
     const uint64_t polStream = l2_policy_evict_first();            // samples stream through L2 once (plus the overlap re-read)
     const uint64_t polKeep = l2_policy_evict_last();               // the per-team Max/Min partials stay L2 resident
 
-    // leader only: fetch frame f of scan sc into the stage buffer.  A bulk copy covers the 16-byte granules around the
-    // frame (offsets can be odd) and is clipped at the end of the batch (see curscan_smem.cuh).
+    // leader only: fetch frame f of scan sc into the stage buffer.  General mode: one bulk copy of the 16-byte granules around
+    // the frame (offsets can be odd), clipped at the end of the batch (see curscan_smem.cuh).  Ring mode (every frame starts
+    // F/2 after the previous one, i.e. 50 % overlap): the stage buffer is two half-frame slots, hop h lives in slot h & 1, and
+    // only the NEW hop of a frame is copied: each sample crosses L2 -> shared memory once.
     const int64_t totalElems = p.nScans * p.scanStride;
+    const bool ring = p.hopRing != 0;
+    constexpr int HALF_BYTES = (F / 2) * SC::EB;
     auto issue = [&](int64_t sc, int f) {
+        if (ring) {
+            const int h = f == 0 ? 0 : f + 1;                      // first hop to fetch
+            const uint32_t bytes = f == 0 ? 2 * HALF_BYTES : HALF_BYTES;
+            const int64_t e0 = sc * p.scanStride + (int64_t)h * (F / 2);
+            mbar_expect_tx(mbar, bytes);
+            tma_load_1d_hint(stage + (h & 1) * HALF_BYTES, reinterpret_cast<const unsigned char*>(p.samples) + e0 * SC::EB, bytes, mbar, polStream);
+            return;
+        }
         constexpr int64_t GM = SC::SLACK > 0 ? SC::SLACK - 1 : 0;
         const int64_t e0 = sc * p.scanStride + foffs[f];
         const int64_t e0a = e0 & ~GM;
@@ -336,10 +377,13 @@ __global__ void __launch_bounds__(R32Cfg::CTA, 1) curscan_r32_kernel(const ScanP
             float2 b[P];
             {
                 mbar_wait(mbar, (uint32_t)(g & 1));
-                const int mis = SC::SLACK > 0 ? (((int)sbase + foffs[f]) & (SC::SLACK - 1)) : 0;
-                const typename IN::raw_t* sp = reinterpret_cast<const typename IN::raw_t*>(stage) + mis + j;
+                const int mis = (SC::SLACK > 0 && !ring) ? (((int)sbase + foffs[f]) & (SC::SLACK - 1)) : 0;
+                const typename IN::raw_t* sp0 = reinterpret_cast<const typename IN::raw_t*>(stage + ((ring && (f & 1)) ? HALF_BYTES : 0)) + mis + j;
+                const typename IN::raw_t* sp1 = reinterpret_cast<const typename IN::raw_t*>(stage + ((ring && (f & 1)) ? 0 : HALF_BYTES)) + mis + j;
 #pragma unroll
-                for (int m = 0; m < P; ++m) b[m] = IN::get(sp[NT * m], u8off);
+                for (int m = 0; m < P / 2; ++m) b[m] = IN::get(sp0[NT * m], u8off);
+#pragma unroll
+                for (int m = 0; m < P / 2; ++m) b[P / 2 + m] = IN::get(sp1[NT * m], u8off);
             }
             // every thread of the team is past its stage reads and (program order) past the previous frame's exchange reads
             sync();
@@ -394,8 +438,8 @@ __global__ void __launch_bounds__(R32Cfg::CTA, 1) curscan_r32_kernel(const ScanP
 #pragma unroll
         for (int m = 0; m < P; ++m) erow[(tid + NT * m) ^ (F >> 1)] = acc[m] * linScale;
         sync();
-        scan_epilogue_rows<NT>(p, erow, scan, valid, it, slot, tid, polKeep);
-        if (p.hm != nullptr) {
+        const bool hmDone = scan_epilogue_rows<NT>(p, erow, scan, valid, it, slot, tid, polKeep);
+        if (p.hm != nullptr && !hmDone) {
             sync();
             // _data_plotcompress (K:184-200): W groups of adjacent bins
             const int W = p.hmW, gsz = F / W;

@@ -195,8 +195,8 @@ __global__ void __launch_bounds__(R32PCfg::CTA, 1) curscan_r32p_kernel(const Sca
 #pragma unroll
             for (int m = 0; m < P; ++m) erow[(tid + NT * m) ^ (F >> 1)] = acc[m] * linScale;
             sync();
-            scan_epilogue_rows<NT>(p, erow, scan, valid, it, slot, tid, polKeep);
-            if (p.hm != nullptr) {
+            const bool hmDone = scan_epilogue_rows<NT>(p, erow, scan, valid, it, slot, tid, polKeep);
+            if (p.hm != nullptr && !hmDone) {
                 sync();
                 const int W = p.hmW, gsz = F / W;
                 float* __restrict__ hm = reinterpret_cast<float*>(p.hm);

@@ -14,6 +14,7 @@
 // the registers that own the bins.  Only the per-scan outputs are written.
 #pragma once
 #include "fft_core.cuh"
+#include "db_math.cuh"
 #include "kspec_internal.h"
 
 namespace kspec {
@@ -136,11 +137,6 @@ __device__ __forceinline__ double kabs(double2 a) {
     const double e = fma(-g, h, 0.5);
     return p > 1e-290 ? fma(g, e, g) : 0.0;
 }
-
-// 10*log10(v) in the float32 fast mode: MUFU.LG2 (abs error 2^-22 in log2 near 1, 2 ulp elsewhere) -> < 2e-5 dB, far inside
-// the 1e-3 dB budget, for ~20 instructions less per bin than log10f.  0 -> -inf as numpy (K:109).
-__device__ __forceinline__ float to_db(float v) { return 3.0102999566398120f * __log2f(v); }
-__device__ __forceinline__ double to_db(double v) { return 10.0 * log10(v); }
 
 template <typename T> __device__ __forceinline__ T pos_inf();
 template <> __device__ __forceinline__ float pos_inf<float>() { return __int_as_float(0x7f800000); }

@@ -7,6 +7,7 @@
 //   linear_epilogue  dB / stats / waterfall for engines that deliver one linear accumulation row per scan.
 //   widen / narrow   T <-> float64 at the ABI boundary.
 #include "kspec_internal.h"
+#include "db_math.cuh"
 #include <math.h>
 
 namespace kspec {
@@ -21,7 +22,7 @@ constexpr int FIN_Y = 16;
 template <typename T>
 __global__ void stats_finish_kernel(const T* __restrict__ wsMax, const T* __restrict__ wsMin, int slots,
                                     const T* __restrict__ avgRows, int avgWin, int F, const double* __restrict__ carry,
-                                    int firstIsSeed, double avgScale, double* __restrict__ out) {
+                                    int firstIsSeed, double avgScale, double* __restrict__ out, int partialsLinear, T gain) {
     __shared__ double shMax[FIN_Y][33], shMin[FIN_Y][33];
     const int j = blockIdx.x * 32 + threadIdx.x;
     const bool inb = j < F;
@@ -39,6 +40,11 @@ __global__ void stats_finish_kernel(const T* __restrict__ wsMax, const T* __rest
     for (int y = 1; y < FIN_Y; ++y) {
         mx = fmax(mx, shMax[y][threadIdx.x]);
         mn = fmin(mn, shMin[y][threadIdx.x]);
+    }
+    if (partialsLinear) {
+        // the R32 kernels reduce the normalised LINEAR amplitudes (the dB map is monotone): the same conversion as the rows get
+        mx = (double)(to_db((T)mx) - gain);
+        mn = (double)(to_db((T)mn) - gain);
     }
     if (carry) {
         mx = fmax(mx, carry[j]);
@@ -319,13 +325,16 @@ inline int nblk(int64_t n, int t) { return (int)((n + t - 1) / t); }
 }  // namespace
 
 void launch_stats_finish(int prec, const void* wsMax, const void* wsMin, int slots, const void* avgRows, int avgWin, int F,
-                         const double* carry, int firstIsSeed, double avgScale, double* out, cudaStream_t st) {
+                         const double* carry, int firstIsSeed, double avgScale, double* out, cudaStream_t st, int partialsLinear,
+                         double gain) {
     if (prec == KSPEC_PREC_F32)
         stats_finish_kernel<float><<<nblk(F, 32), dim3(32, FIN_Y), 0, st>>>((const float*)wsMax, (const float*)wsMin, slots,
-                                                                 (const float*)avgRows, avgWin, F, carry, firstIsSeed, avgScale, out);
+                                                                 (const float*)avgRows, avgWin, F, carry, firstIsSeed, avgScale, out,
+                                                                 partialsLinear, (float)gain);
     else
         stats_finish_kernel<double><<<nblk(F, 32), dim3(32, FIN_Y), 0, st>>>((const double*)wsMax, (const double*)wsMin, slots,
-                                                                  (const double*)avgRows, avgWin, F, carry, firstIsSeed, avgScale, out);
+                                                                  (const double*)avgRows, avgWin, F, carry, firstIsSeed, avgScale, out,
+                                                                  partialsLinear, gain);
 }
 
 void launch_widen(int prec, const void* src, double* dst, int64_t n, cudaStream_t st) {

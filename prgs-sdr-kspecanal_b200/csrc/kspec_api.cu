@@ -71,7 +71,7 @@ struct kspec_plan {
     SmemKernelInfo kiMulti{};     // multi-team variant (ctasPerSm == 0: not available for this shape)
     SmemKernelInfo kiR32{};       // 32 x 2 x 32 layout (fftSize 2048, float32, uint8 / complex64 ingest)
     bool r32Off = false;          // KSPEC_NO_R32=1 at plan creation: keep the 16/16/8 layouts (A/B runs, tests)
-    bool r32Pipe = false;         // kiR32 describes the two-role pipeline (curscan_r32p.cuh); KSPEC_R32_SERIAL=1 selects the one-role kernel
+    bool r32Pipe = false;         // KSPEC_R32_PIPE=1 at plan creation: the two-role pipeline (curscan_r32p.cuh) instead of the one-role kernel; kiR32 describes it
     int64_t convSize = 0;
     BigFft* big = nullptr;
     MixedRadix* mixed = nullptr;
@@ -135,7 +135,8 @@ ScanParams base_params(const kspec_plan* pl, const void* dSamples, int64_t nScan
 }
 
 // run the FFT engine + per-scan epilogue described by p (rows/stats/hm pointers already set); slots out
-int run_engine(kspec_plan* pl, ScanParams& p, int* slotsOut) {
+int run_engine(kspec_plan* pl, ScanParams& p, int* slotsOut, int* statsLinear = nullptr) {
+    if (statsLinear) *statsLinear = 0;
     const size_t rb = real_bytes(pl->prec);
     if (pl->path == KSPEC_PATH_SMEM) {
         const int nFrames = (int)pl->offs.size();
@@ -214,6 +215,12 @@ int run_engine(kspec_plan* pl, ScanParams& p, int* slotsOut) {
         }
         const int ks = (int)(pl->kcount % kspec_plan::KT);
         cudaEventRecord(pl->kev[ks][0], pl->st);
+        if (r32) {
+            // ring staging: uniform hop of half a frame (50 % overlap) and 16-byte aligned scans
+            bool ring = ((size_t)pl->S * in_elem_bytes(pl->inFmt)) % 16 == 0 && ((uintptr_t)p.samples % 16) == 0 && !pl->r32Pipe;
+            for (size_t f = 0; ring && f < pl->offs.size(); ++f) ring = pl->offs[f] == (int64_t)f * (pl->F / 2);
+            p.hopRing = ring ? 1 : 0;
+        }
         int e;
         if (r32 && pl->r32Pipe) e = pl->inFmt == KSPEC_IN_U8_IQ ? launch_r32p_u8(p, grid, pl->st, nullptr) : launch_r32p_c64(p, grid, pl->st, nullptr);
         else if (r32) e = pl->inFmt == KSPEC_IN_U8_IQ ? launch_r32_u8(p, grid, pl->st, nullptr) : launch_r32_c64(p, grid, pl->st, nullptr);
@@ -223,6 +230,7 @@ int run_engine(kspec_plan* pl, ScanParams& p, int* slotsOut) {
         if (e != 0) { set_error("scan kernel launch failed: %s", cudaGetErrorString((cudaError_t)e)); return KSPEC_ERR_CUDA; }
         pl->launches += 1;
         *slotsOut = slots;
+        if (statsLinear) *statsLinear = r32 ? 1 : 0;          // the R32 kernels keep their Max/Min partials in the linear domain
         return KSPEC_OK;
     }
     // big engines: un-normalised accumulation rows, then a shared epilogue
@@ -435,9 +443,9 @@ int kspec_plan_create(kspec_plan** out, int fftSize, int64_t fullSize, double no
         if (pl->ki.ctasPerSm < 1) { set_error("fused kernel for fftSize %d does not fit on this device", fftSize); return fail(KSPEC_ERR_UNSUPPORTED); }
         if (precision == KSPEC_PREC_F32 && pl->log2F == 11 && inFmt != KSPEC_IN_C128) {
             const char* no = getenv("KSPEC_NO_R32");
-            const char* ser = getenv("KSPEC_R32_SERIAL");
+            const char* pipe = getenv("KSPEC_R32_PIPE");
             pl->r32Off = no && no[0] == '1';
-            pl->r32Pipe = !(ser && ser[0] == '1');
+            pl->r32Pipe = pipe && pipe[0] == '1';
             int e = pl->r32Pipe ? (inFmt == KSPEC_IN_U8_IQ ? launch_r32p_u8(dummy, 0, pl->st, &pl->kiR32) : launch_r32p_c64(dummy, 0, pl->st, &pl->kiR32)) : 1;
             if (e != 0 || pl->kiR32.ctasPerSm < 1) {
                 cudaGetLastError();
@@ -521,10 +529,10 @@ int zerospan_part(kspec_plan* pl, const void* dSamples, int64_t nScans, int64_t 
     if ((rc = pl->avgRows.reserve((size_t)p.avgWin * F * rb))) return rc;
     p.avgRows = pl->avgRows.p;
     if (haveAdj) p.adj = pl->adj.p;
-    int slots = 0;
-    if ((rc = run_engine(pl, p, &slots))) return rc;
+    int slots = 0, statsLinear = 0;
+    if ((rc = run_engine(pl, p, &slots, &statsLinear))) return rc;
     launch_stats_finish(pl->prec, pl->wsMax.p, pl->wsMin.p, slots, pl->avgRows.p, p.avgWin, F, dCarry, firstIsSeed, avgScale,
-                        (double*)pl->stats.p, pl->st);
+                        (double*)pl->stats.p, pl->st, statsLinear, gain);
     pl->launches += 1;
     CK(cudaGetLastError());
     return KSPEC_OK;

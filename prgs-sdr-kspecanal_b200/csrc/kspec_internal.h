@@ -42,6 +42,7 @@ struct ScanParams {
     // linear-row engines only: accumulation rows stored [k1][k2] with bin k = k1 + 2^accL1 * k2 (0: natural order)
     int32_t accL1, accL2;
     int32_t accShifted;        // acc rows are already fftshift-ed and normalised (zeroSpanPlay records)
+    int32_t hopRing;           // R32 kernels: every frame starts fftSize/2 after the previous one and scans are 16-byte aligned
 };
 
 struct SmemKernelInfo { int ctaThreads, smemBytes, teams, ctasPerSm, stages; };
@@ -72,7 +73,8 @@ constexpr int AVG_WINDOW = 64;   // rows that can still influence the float64 ha
 // Max/Min over the per-team partials (+ carry), Avg recurrence over the last rows (+ carry), scaled for sharding.
 void launch_stats_finish(int prec, const void* wsMax, const void* wsMin, int slots, const void* avgRows, int avgWin,
                          int F, const double* carry /*3F or null*/, int firstIsSeed, double avgScale,
-                         double* out /*3F*/, cudaStream_t st);
+                         double* out /*3F*/, cudaStream_t st, int partialsLinear = 0 /*partials hold linear amplitudes*/,
+                         double gain = 0.0);
 // T -> float64 widening of result rows
 void launch_widen(int prec, const void* src, double* dst, int64_t n, cudaStream_t st);
 // float64 host-side vectors -> T

@@ -272,7 +272,7 @@ def test_large_batch_layout_ragged(fmt):
                                   state=(first["max"], first["min"], first["avg"]))              # large batch: four teams per CTA
         # plan.info describes what the largest batches run: the 32 x 2 x 32 layout (uint8 / complex64 ingest) or four teams
         if fmt != "c128":
-            assert plan.info.cta_threads == 512 and plan.info.scans_per_cta == 4
+            assert plan.info.cta_threads == 384 and plan.info.scans_per_cta == 6
     lin = [O.curscan(xin[k * S:(k + 1) * S], F, r, win) for k in range(n)]
     ref = O.zerospan(lin, gain, xres, "MAX")
     assert np.max(np.abs(got["rows"] - ref["cur_rows"][40:])) < DB_TOL
@@ -303,7 +303,7 @@ def test_r32_layout_ragged(fmt, cumu, r, wname):
         xin = raw.astype(np.complex128)
     per = 2 * S if fmt == "u8" else S
     with Plan(F, S, r, win, cumu, _ffi.in_format(raw), precision="f32") as plan:
-        assert plan.info.cta_threads == 512 and plan.info.scans_per_cta == 4
+        assert plan.info.cta_threads == 384 and plan.info.scans_per_cta == 6
         first = plan.zerospan_batch(raw[:3 * per], 3, gain, xres, "MAX")                         # small batch: base layout
         got = plan.zerospan_batch(raw[3 * per:], n - 3, gain, xres, "MAX", rows="db",
                                   state=(first["max"], first["min"], first["avg"]))              # large batch: 32 x 2 x 32
