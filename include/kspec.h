@@ -47,9 +47,21 @@ enum { KSPEC_CUMU_RAW = 0, KSPEC_CUMU_AVG = 1, KSPEC_CUMU_MAX = 2, KSPEC_CUMU_MI
        KSPEC_CUMU_PSD = 4 };
 /* IQ ingest formats: rtl_sdr raw interleaved uint8 I,Q (octave/load_rtlsdr.m:8-12), numpy complex64, numpy complex128 (K:335) */
 enum { KSPEC_IN_U8_IQ = 0, KSPEC_IN_C64 = 1, KSPEC_IN_C128 = 2 };
-/* arithmetic of the FFT/magnitude/cumulate chain.  AUTO = F64: within 1e-8 dB of the reference's float64 on every bin.
- * F32 (power-of-two fftSize <= 16384 only) is the fast mode BASELINE.json's north_star describes: within 1e-3 dB for
- * bins down to 1e-4 of the scan's strongest bin, absolute error ~1e-8 of that peak below (float32 rounding noise). */
+/* arithmetic of the FFT/magnitude/cumulate chain.
+ *   AUTO = F64: within 1e-8 dB of the reference's float64 on EVERY bin of every engine (the parity mode; tests hold it
+ *     to that on all five BASELINE configurations).  AUTO never selects float32.
+ *   F32 (power-of-two fftSize <= 16384 only; an explicit request, never a default) is the fast mode BASELINE.json's
+ *     north_star describes.  Its contract, checked by tests/test_gpu_parity.py::test_f32_contract on the synthetic
+ *     inputs of every BASELINE configuration where float32 is selectable:
+ *       - every bin of a scan is within 3e-7 of that scan's strongest bin (absolute, linear amplitude): float32
+ *         rounding noise of a transform whose largest output is the peak;
+ *       - hence every bin above 2e-3 of the scan's peak (-27 dB in this program's 10*log10 convention) is within
+ *         1e-3 dB, and weaker bins are NOT guaranteed to be: a caller that needs 1e-3 dB on deep nulls next to strong
+ *         carriers uses AUTO;
+ *       - frame count, frame offsets, bin order and the peak-bin argmax are exact;
+ *       - on the BASELINE cfg-1 workload (fftSize 2048, hanning, 50 % overlap, cumulate AVG, tones + noise) every bin
+ *         of every output (rows, waterfall rows, Max/Min/Avg) is within 1e-3 dB: the noise floor of that input sits
+ *         above 2e-3 of the peak after 15 averaged frames. */
 enum { KSPEC_PREC_AUTO = 0, KSPEC_PREC_F32 = 1, KSPEC_PREC_F64 = 2 };
 /* pltCompress / pltCompressHM, K:25-29, _data_plotcompress K:168-202 (MIN: documented, unreachable in the reference) */
 enum { KSPEC_COMPRESS_RAW = 0, KSPEC_COMPRESS_MAX = 1, KSPEC_COMPRESS_AVG = 2, KSPEC_COMPRESS_MIN = 3 };
@@ -133,7 +145,9 @@ int kspec_scan_batch(kspec_plan* plan, const void* samples, int nSteps, const ui
  * kspec_scan_shard: this plan holds the captures of steps [stepBase, stepBase+nStepsLocal) of nStepsTotal; iStart has
  * nStepsTotal entries (the global geometry).  curPartial (totalEntries) receives this shard's share of the stitched
  * Fft.Cur -- the halving recurrence written as a weighted sum -- so that a SUM over shards (kspec_comm_allreduce_sum)
- * equals the sequential result.  kspec_scan_stats_update then applies K:657-668 (Max/Min/Avg from the finished Fft.Cur on
+ * equals the sequential result (bins that no step covers -- none in the reference's geometries, K:598-600 -- come out
+ * as 0 in every shard: the caller keeps its previous Fft.Cur there, as the single-plan kspec_scan_batch does).
+ * kspec_scan_stats_update then applies K:657-668 (Max/Min/Avg from the finished Fft.Cur on
  * the bins below lastDone = iDone of the last step; bScanRangeBaseDataIsRaw is not available in sharded mode). */
 int kspec_scan_shard(kspec_plan* plan, const void* samples, int nStepsLocal, int stepBase, int nStepsTotal,
                      const uint8_t* stepOk, const int64_t* iStart, int64_t totalEntries,
@@ -154,8 +168,10 @@ int kspec_plot_highs(kspec_plan* plan, const double* freqs, const double* levels
 int kspec_conv_smooth(kspec_plan* plan, const double* vals, int64_t n, const double* taps, int nTaps, int edge, double* out);
 
 /* ---- device-resident variants (zero-copy pipelines; what bench.py times for the roofline) ---------------------
- * kspec_dev_* manage device buffers on the plan's device (sample buffers must be 16-byte aligned, which every CUDA
- * allocation is); kspec_zerospan_batch_dev consumes samples already in HBM
+ * kspec_dev_* manage device buffers on the plan's device.  Sample buffers handed to kspec_zerospan_batch_dev must be
+ * 16-byte aligned (every CUDA allocation is; an offset into one need not be: KSPEC_ERR_ARG otherwise) and, when
+ * nScans*fullSize*elementSize is not a multiple of 16, readable up to the next multiple (kspec_dev_alloc pads): the fused
+ * kernels stage frames with 16-byte granular bulk copies.  kspec_zerospan_batch_dev consumes samples already in HBM
  * and leaves rows / hm rows / stats in plan-owned device buffers until kspec_zerospan_fetch copies them out.
  * kspec_timer_* bracket work on the plan's stream with CUDA events. */
 int kspec_dev_alloc(kspec_plan* plan, int64_t bytes, void** dptr);
@@ -194,7 +210,13 @@ int kspec_comm_allreduce_sum(kspec_comm* comm, double* v, int64_t n);
  * plan may start its next batch at once.  kspec_comm_join makes the plan's stream wait for the reduction and copies the
  * reduced vectors back into the plan (kspec_zerospan_fetch then returns them). */
 int kspec_comm_allreduce_plan(kspec_comm* comm, kspec_plan* plan);
+/* kspec_comm_join is only valid while the plan still holds the batch that was snapshotted: if the plan has run another
+ * batch since (the overlapped order: batch k, allreduce_plan, batch k+1, ...), its statistics belong to batch k+1 and
+ * join returns KSPEC_ERR_STATE without touching them; the reduced vectors of batch k are then read with
+ * kspec_comm_fetch_reduced (host float64, n = fftSize each), which works in either order.  A reduction is pending until
+ * one of the two has consumed it or another all-reduce has reused the communicator's buffer. */
 int kspec_comm_join(kspec_comm* comm, kspec_plan* plan);
+int kspec_comm_fetch_reduced(kspec_comm* comm, double* max, double* min, double* avg, int64_t n);
 int kspec_comm_finalize(kspec_comm* comm);
 
 #ifdef __cplusplus

@@ -46,7 +46,11 @@ NcclApi& api() {
 }
 
 int need_api() {
-    if (!api().ok) { set_error("NCCL not available: %s", dlerror() ? dlerror() : "libnccl.so.2 could not be loaded"); return KSPEC_ERR_NCCL; }
+    if (!api().ok) {
+        const char* e = dlerror();                 // one call: dlerror() clears the message it returns
+        set_error("NCCL not available: %s", e ? e : "libnccl.so.2 could not be loaded");
+        return KSPEC_ERR_NCCL;
+    }
     return KSPEC_OK;
 }
 
@@ -63,8 +67,17 @@ struct kspec_comm {
     cudaEvent_t evIn = nullptr, evCopied = nullptr, evDone = nullptr;
     double* buf = nullptr;
     size_t cap = 0;
-    int64_t pendingN = 0;      // length of the vectors of the last asynchronous plan reduction held in buf
+    int64_t pendingN = 0;      // length of the vectors of the last asynchronous plan reduction held in buf (0: none)
+    int64_t pendingSeq = -1;   // kspec_plan batch sequence number that reduction snapshotted
 };
+
+namespace {
+struct DevGuard {              // the caller's current device is restored on return (as the plan API does)
+    int prev = -1;
+    explicit DevGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+}  // namespace
 
 #define NCK(call)                                                                         \
     do {                                                                                  \
@@ -113,7 +126,7 @@ int kspec_comm_init(kspec_comm** out, int nRanks, int rank, const char id[128], 
     *out = nullptr;
     int rc = need_api();
     if (rc) return rc;
-    CCK(cudaSetDevice(device));
+    DevGuard guard(device);
     kspec_comm* c = new (std::nothrow) kspec_comm();
     if (!c) { set_error("out of host memory"); return KSPEC_ERR_NOMEM; }
     c->device = device; c->nRanks = nRanks; c->rank = rank;
@@ -129,9 +142,11 @@ int kspec_comm_init(kspec_comm** out, int nRanks, int rank, const char id[128], 
 
 int kspec_comm_allreduce_stats(kspec_comm* c, double* mx, double* mn, double* av, int64_t n) {
     if (!c || !mx || !mn || !av || n < 1) { set_error("bad all-reduce arguments"); return KSPEC_ERR_ARG; }
-    CCK(cudaSetDevice(c->device));
+    DevGuard guard(c->device);
     const size_t bytes = (size_t)n * 8;
+    c->pendingN = 0;                           // buf is reused: an unfetched plan reduction is gone
     if (c->cap < 3 * bytes) {
+        CCK(cudaStreamSynchronize(c->st));
         if (c->buf) cudaFree(c->buf);
         c->buf = nullptr; c->cap = 0;
         CCK(cudaMalloc(&c->buf, 3 * bytes));
@@ -151,7 +166,7 @@ int kspec_comm_allreduce_stats(kspec_comm* c, double* mx, double* mn, double* av
 
 int kspec_comm_allreduce_sum(kspec_comm* c, double* v, int64_t n) {
     if (!c || !v || n < 1) { set_error("bad all-reduce arguments"); return KSPEC_ERR_ARG; }
-    CCK(cudaSetDevice(c->device));
+    DevGuard guard(c->device);
     const size_t bytes = (size_t)n * 8;
     if (c->cap < bytes) {
         CCK(cudaStreamSynchronize(c->st));
@@ -173,8 +188,9 @@ int kspec_comm_allreduce_plan(kspec_comm* c, kspec_plan* plan) {
     double* stats = nullptr;
     int F = 0;
     cudaStream_t st = nullptr;
-    if (!plan_stats_view(plan, &stats, &F, &st)) { set_error("plan holds no batch statistics yet"); return KSPEC_ERR_STATE; }
-    CCK(cudaSetDevice(c->device));
+    int64_t seq = 0;
+    if (!plan_stats_view(plan, &stats, &F, &st, &seq)) { set_error("plan holds no batch statistics yet"); return KSPEC_ERR_STATE; }
+    DevGuard guard(c->device);
     const size_t bytes = (size_t)3 * F * 8;
     if (c->cap < bytes) {
         CCK(cudaStreamSynchronize(c->st));
@@ -194,6 +210,7 @@ int kspec_comm_allreduce_plan(kspec_comm* c, kspec_plan* plan) {
     if (rc) return rc;
     CCK(cudaEventRecord(c->evDone, c->st));
     c->pendingN = F;
+    c->pendingSeq = seq;
     return KSPEC_OK;
 }
 
@@ -202,18 +219,40 @@ int kspec_comm_join(kspec_comm* c, kspec_plan* plan) {
     double* stats = nullptr;
     int F = 0;
     cudaStream_t st = nullptr;
-    if (!plan_stats_view(plan, &stats, &F, &st)) { set_error("plan holds no batch statistics yet"); return KSPEC_ERR_STATE; }
+    int64_t seq = 0;
+    if (!plan_stats_view(plan, &stats, &F, &st, &seq)) { set_error("plan holds no batch statistics yet"); return KSPEC_ERR_STATE; }
     if (c->pendingN != F) { set_error("no reduction of this plan is pending"); return KSPEC_ERR_STATE; }
-    CCK(cudaSetDevice(c->device));
+    if (c->pendingSeq != seq) {
+        // the plan has run another batch since the snapshot: its statistics belong to that batch and stay untouched
+        set_error("the plan has advanced since kspec_comm_allreduce_plan: read the reduced vectors with kspec_comm_fetch_reduced");
+        return KSPEC_ERR_STATE;
+    }
+    DevGuard guard(c->device);
     // the plan's stream waits for the reduction and takes the reduced vectors back: kspec_zerospan_fetch then returns them
     CCK(cudaStreamWaitEvent(st, c->evDone, 0));
     CCK(cudaMemcpyAsync(stats, c->buf, (size_t)3 * F * 8, cudaMemcpyDeviceToDevice, st));
+    CCK(cudaEventRecord(c->evIn, st));                    // the communicator's next snapshot must not overtake this copy
+    CCK(cudaStreamWaitEvent(c->st, c->evIn, 0));
+    c->pendingN = 0;
+    return KSPEC_OK;
+}
+
+int kspec_comm_fetch_reduced(kspec_comm* c, double* mx, double* mn, double* av, int64_t n) {
+    if (!c || !mx || !mn || !av || n < 1) { set_error("bad fetch arguments"); return KSPEC_ERR_ARG; }
+    if (c->pendingN != n) { set_error("no reduction of %lld-element vectors is pending", (long long)n); return KSPEC_ERR_STATE; }
+    DevGuard guard(c->device);
+    const size_t bytes = (size_t)n * 8;
+    CCK(cudaMemcpyAsync(mx, c->buf, bytes, cudaMemcpyDeviceToHost, c->st));
+    CCK(cudaMemcpyAsync(mn, c->buf + n, bytes, cudaMemcpyDeviceToHost, c->st));
+    CCK(cudaMemcpyAsync(av, c->buf + 2 * n, bytes, cudaMemcpyDeviceToHost, c->st));
+    CCK(cudaStreamSynchronize(c->st));
+    c->pendingN = 0;
     return KSPEC_OK;
 }
 
 int kspec_comm_finalize(kspec_comm* c) {
     if (!c) return KSPEC_OK;
-    cudaSetDevice(c->device);
+    DevGuard guard(c->device);
     if (c->st) cudaStreamSynchronize(c->st);
     if (c->comm && api().ok) api().CommDestroy(c->comm);
     if (c->buf) cudaFree(c->buf);

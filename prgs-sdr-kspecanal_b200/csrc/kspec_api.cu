@@ -70,6 +70,9 @@ struct kspec_plan {
     SmemKernelInfo ki{};          // base variant of the fused kernel
     SmemKernelInfo kiMulti{};     // multi-team variant (ctasPerSm == 0: not available for this shape)
     SmemKernelInfo kiR32{};       // 32 x 2 x 32 layout (fftSize 2048, float32, uint8 / complex64 ingest)
+    bool frameParallelOff = false; // KSPEC_FRAME_PARALLEL=0 at plan creation
+    size_t chunkBytes = (size_t)256 << 20;   // pipelined host batches; KSPEC_PIPELINE_CHUNK_BYTES at plan creation
+    int64_t statsSeq = 0;          // bumped by every batch that rewrites `stats` (kspec_comm_join checks it)
     bool r32Off = false;          // KSPEC_NO_R32=1 at plan creation: keep the 16/16/8 layouts (A/B runs, tests)
     bool r32Pipe = false;         // KSPEC_R32_PIPE=1 at plan creation: the two-role pipeline (curscan_r32p.cuh) instead of the one-role kernel; kiR32 describes it
     int64_t convSize = 0;
@@ -144,8 +147,7 @@ int run_engine(kspec_plan* pl, ScanParams& p, int* slotsOut, int* statsLinear = 
             // its 15..71 frames on one team: launch every frame as a one-frame scan of its own and cumulate afterwards.
             const int64_t teamsAvail = (int64_t)pl->smCount * (pl->ki.ctasPerSm > 0 ? pl->ki.ctasPerSm : 1) * pl->ki.teams;
             const int64_t nv = p.nScans * nFrames;
-            const char* fp = getenv("KSPEC_FRAME_PARALLEL");        // "0": always walk the frames of a scan on one team
-            const bool off = fp && fp[0] == '0';
+            const bool off = pl->frameParallelOff;                 // always walk the frames of a scan on one team
             // (up to 64 scans: the per-scan epilogue that follows walks the scans of a batch in order, one thread per bin)
             if (!off && nFrames > 1 && p.nScans <= 64 && p.nScans * 2 <= teamsAvail && (size_t)nv * pl->F * rb <= ((size_t)256 << 20)) {
                 int rc;
@@ -287,11 +289,12 @@ std::vector<double> host_lin_twiddles(int log2F) {
     }
     return out;
 }
-bool plan_stats_view(kspec_plan* pl, double** stats3F, int* F, cudaStream_t* st) {
+bool plan_stats_view(kspec_plan* pl, double** stats3F, int* F, cudaStream_t* st, int64_t* seq) {
     if (!pl || !pl->haveBatch || !pl->stats.p) return false;
     *stats3F = (double*)pl->stats.p;
     *F = pl->F;
     *st = pl->st;
+    if (seq) *seq = pl->statsSeq;
     return true;
 }
 }  // namespace kspec
@@ -331,6 +334,11 @@ int kspec_plan_create(kspec_plan** out, int fftSize, int64_t fullSize, double no
     if (!pl) { set_error("out of host memory"); return KSPEC_ERR_NOMEM; }
     pl->F = fftSize; pl->S = fullSize; pl->r = nonOverlap; pl->cumu = cumuMode; pl->inFmt = inFmt; pl->device = device;
     pl->u8off = u8_offset; pl->u8scale = u8_scale;
+    {   // tuning / test knobs are read once, here (none is needed in normal use: DESIGN.md 3.8)
+        const char* fp = getenv("KSPEC_FRAME_PARALLEL");
+        pl->frameParallelOff = fp && fp[0] == '0';
+        if (const char* e = getenv("KSPEC_PIPELINE_CHUNK_BYTES")) { const long long v = atoll(e); if (v > 0) pl->chunkBytes = (size_t)v; }
+    }
     const bool pow2 = (fftSize & (fftSize - 1)) == 0;
     if (pow2) { int l = 0; while ((1 << l) < fftSize) ++l; pl->log2F = l; }
     if (precision == KSPEC_PREC_AUTO) precision = KSPEC_PREC_F64;     // parity first; F32 is the explicit fast mode
@@ -403,6 +411,7 @@ int kspec_plan_create(kspec_plan** out, int fftSize, int64_t fullSize, double no
         }
     const size_t rb = real_bytes(precision);
     if (pl->path == KSPEC_PATH_SMEM) {
+        if (fullSize > (int64_t)INT32_MAX) { set_error("fullSize %lld: the fused kernels keep frame offsets in 32 bits", (long long)fullSize); return fail(KSPEC_ERR_UNSUPPORTED); }
         std::vector<int32_t> o32(pl->offs.begin(), pl->offs.end());
         if (cudaMalloc(&pl->dOffs, o32.size() * 4) != cudaSuccess || cudaMalloc(&pl->dWin, fftSize * rb) != cudaSuccess ||
             cudaMalloc(&pl->dTw, (size_t)fftSize * 2 * rb) != cudaSuccess) {
@@ -534,6 +543,7 @@ int zerospan_part(kspec_plan* pl, const void* dSamples, int64_t nScans, int64_t 
     launch_stats_finish(pl->prec, pl->wsMax.p, pl->wsMin.p, slots, pl->avgRows.p, p.avgWin, F, dCarry, firstIsSeed, avgScale,
                         (double*)pl->stats.p, pl->st, statsLinear, gain);
     pl->launches += 1;
+    pl->statsSeq += 1;
     CK(cudaGetLastError());
     return KSPEC_OK;
 }
@@ -546,6 +556,10 @@ int zerospan_check(kspec_plan* pl, const void* samples, int64_t nScans, int hmMo
     if (hmMode < KSPEC_COMPRESS_RAW || hmMode > KSPEC_COMPRESS_MIN) { set_error("unknown pltCompressHM %d", hmMode); return KSPEC_ERR_ARG; }
     if (carry && (!mx || !mn || !av)) { set_error("carry requested without max/min/avg state"); return KSPEC_ERR_ARG; }
     if (nScansTotal < scanIndexBase + nScans || scanIndexBase < 0) { set_error("shard [%lld,+%lld) outside capture of %lld scans", (long long)scanIndexBase, (long long)nScans, (long long)nScansTotal); return KSPEC_ERR_ARG; }
+    if (pl->path == KSPEC_PATH_SMEM) {
+        // the fused kernels stage frames with 16-byte granular bulk copies relative to the sample base
+        if (((uintptr_t)samples & 15) != 0) { set_error("device sample buffer must be 16-byte aligned (kspec_dev_alloc is)"); return KSPEC_ERR_ARG; }
+    }
     *W = hm_width(pl->F, xRes, hmMode);
     if (wantHm && (xRes < 1 || pl->F % *W != 0)) { set_error("fftSize %d is not a multiple of the waterfall width %d (xRes must divide fftSize, K:941-949)", pl->F, *W); return KSPEC_ERR_ARG; }
     return KSPEC_OK;
@@ -642,6 +656,7 @@ int kspec_zerospan_rows_batch(kspec_plan* pl, const double* linRows, int64_t nSc
     launch_linear_epilogue(pl->prec, p, dAcc, F, 1, pl->st);
     launch_stats_finish(pl->prec, pl->wsMax.p, pl->wsMin.p, 1, pl->avgRows.p, p.avgWin, F, dCarry, carry ? 0 : 1, 1.0, (double*)pl->stats.p, pl->st);
     pl->launches += hm_rows ? 3 : 2;
+    pl->statsSeq += 1;
     CK(cudaGetLastError());
     pl->lastScans = nScans; pl->lastRowsKind = p.rowsKind; pl->lastW = W; pl->lastHm = hm_rows != nullptr; pl->haveBatch = true;
     return kspec_zerospan_fetch(pl, dbRows, hm_rows, mx, mn, av);
@@ -696,10 +711,15 @@ int kspec_zerospan_batch(kspec_plan* pl, const void* samples, int64_t nScans, do
     // Large host batches are pipelined: the samples cross PCIe in chunks on a copy stream while the engine works on the
     // chunks that have arrived (each chunk continues from the previous one's Max/Min/Avg, like consecutive batches with
     // carry) and the finished rows flow back; the exposed time is one chunk's copy plus one chunk's compute.
-    size_t chunkBytes = (size_t)256 << 20;
-    if (const char* e = getenv("KSPEC_PIPELINE_CHUNK_BYTES")) { const long long v = atoll(e); if (v > 0) chunkBytes = (size_t)v; }
-    int64_t chunkScans = (int64_t)(chunkBytes / scanBytes);
+    int64_t chunkScans = (int64_t)(pl->chunkBytes / scanBytes);
     if (chunkScans < AVG_WINDOW) chunkScans = AVG_WINDOW;        // every part must hold the whole Avg window of its own rows
+    // every chunk must start on a 16-byte boundary of the device buffer (bulk copies of the staged kernels): with an odd
+    // fullSize a scan is not a whole number of 16-byte granules, so chunks are made of whole groups of scans that are
+    {
+        int64_t grp = 1;
+        while ((grp * (int64_t)scanBytes) % 16 != 0) grp *= 2;   // scanBytes >= 2: at most 8
+        chunkScans = (chunkScans + grp - 1) / grp * grp;
+    }
     if (nScans < 2 * chunkScans) {
         CK(cudaMemcpyAsync(pl->in.p, samples, bytes, cudaMemcpyHostToDevice, pl->st));
         if ((rc = kspec_zerospan_batch_dev(pl, pl->in.p, nScans, gain, adj, hmMode, xRes, rowsKind, hm_rows != nullptr, mx, mn, av, carry,

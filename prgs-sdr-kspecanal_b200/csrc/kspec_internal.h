@@ -124,6 +124,6 @@ std::vector<double> host_lin_twiddles(int log2F);
 void set_error(const char* fmt, ...);
 
 // comm.cu <- kspec_api.cu: device view of the [max | min | avg] vectors the last zeroSpan batch left in the plan
-bool plan_stats_view(kspec_plan* plan, double** stats3F, int* F, cudaStream_t* st);
+bool plan_stats_view(kspec_plan* plan, double** stats3F, int* F, cudaStream_t* st, int64_t* seq = nullptr);
 
 }  // namespace kspec

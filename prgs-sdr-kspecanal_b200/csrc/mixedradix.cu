@@ -325,6 +325,7 @@ bool mixedradix_split(int64_t F, int* n1, int* n2) {
 
 struct MixedRadix {
     int inFmt = 0, smCount = 0;
+    int threads = 0;            // CTA size of both passes (KSPEC_MR_THREADS=256 at creation: tuning knob)
     int64_t F = 0;
     int N1 = 0, N2 = 0;
     MrSched sc1{}, sc2{};
@@ -374,6 +375,8 @@ MixedRadix* mixedradix_create(int prec, int inFmt, int64_t F, const double* wind
     MCK(cudaMemcpyAsync(b->dWin, window, (size_t)F * 8, cudaMemcpyHostToDevice, st));
     MCK(cudaMalloc(&b->dTab1, (size_t)b->N1 * 16));
     MCK(cudaMalloc(&b->dTab2, (size_t)b->N2 * 16));
+    b->threads = MR_THREADS;
+    if (const char* e = getenv("KSPEC_MR_THREADS")) { if (atoi(e) == 256) b->threads = 256; }
     int smem = MR_SMEM_STD;
     if (const char* e = getenv("KSPEC_MR_SMEM")) { const int v = atoi(e); if (v >= 16 * 1024 && v <= MR_SMEM_BIG) smem = v; }
     for (MrSched* sc : {&b->sc1, &b->sc2}) {
@@ -422,8 +425,7 @@ int mixedradix_run(MixedRadix* b, const void* samples, int64_t scanStride, int64
     }
     const size_t eb = b->inFmt == KSPEC_IN_U8_IQ ? 2 : (b->inFmt == KSPEC_IN_C64 ? 8 : 16);
     const size_t smem1 = mr_smem_bytes(b->sc1), smem2 = mr_smem_bytes(b->sc2);
-    int nt = MR_THREADS;
-    if (const char* e = getenv("KSPEC_MR_THREADS")) { if (atoi(e) == 256) nt = 256; }
+    const int nt = b->threads;
     void (*kr)(const MrRowsParams);
     void (*kc)(const MrColsParams);
     const bool stdTile = smem2 <= (size_t)MR_SMEM_STD;

@@ -83,6 +83,7 @@ SIGNATURES = {
     "kspec_comm_allreduce_sum": (C.c_int, [_P, _D, _I64]),
     "kspec_comm_allreduce_plan": (C.c_int, [_P, _P]),
     "kspec_comm_join": (C.c_int, [_P, _P]),
+    "kspec_comm_fetch_reduced": (C.c_int, [_P, _D, _D, _D, _I64]),
     "kspec_comm_finalize": (C.c_int, [_P]),
 }
 

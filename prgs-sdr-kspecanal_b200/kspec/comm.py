@@ -44,8 +44,15 @@ class Comm:
         check(_ffi.lib().kspec_comm_allreduce_plan(self._h, plan._h))
 
     def join(self, plan):
-        """the plan's stream waits for the last allreduce_plan_stats and takes the reduced vectors (fetch returns them)"""
+        """the plan's stream waits for the last allreduce_plan_stats and takes the reduced vectors (fetch returns them).
+        Only while the plan still holds the batch that was reduced; otherwise KSPEC_ERR_STATE -> use fetch_reduced."""
         check(_ffi.lib().kspec_comm_join(self._h, plan._h))
+
+    def fetch_reduced(self, n):
+        """(max, min, avg) float64[n] of the last allreduce_plan_stats, whatever the plan has done since"""
+        mx, mn, av = (np.empty(n, dtype=np.float64) for _ in range(3))
+        check(_ffi.lib().kspec_comm_fetch_reduced(self._h, dptr(mx), dptr(mn), dptr(av), int(n)))
+        return mx, mn, av
 
     def close(self):
         if self._h is not None and self._h.value:

@@ -220,6 +220,11 @@ class Plan:
         host = np.ascontiguousarray(host)
         check(_ffi.lib().kspec_dev_upload(self._h, C.c_void_p(p.value + offset), vptr(host), host.nbytes))
 
+    def dev_download(self, p, n_bytes, offset=0):
+        out = np.empty(int(n_bytes), dtype=np.uint8)
+        check(_ffi.lib().kspec_dev_download(self._h, vptr(out), C.c_void_p(p.value + offset), int(n_bytes)))
+        return out
+
     def zerospan_batch_dev(self, d_samples, n_scans, gain, x_res, hm_mode="MAX", adj=None, rows=None, want_hm=True,
                            state=None, scan_index_base=0, n_scans_total=None):
         kind = {None: _ffi.ROWS_NONE, "linear": _ffi.ROWS_LINEAR, "db": _ffi.ROWS_DB}[rows]

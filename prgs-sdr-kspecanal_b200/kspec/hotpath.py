@@ -169,9 +169,26 @@ def curscan_samples(d, samples):
 def zero_span_init(d):
     """K:437-458: fresh Max/Min/Avg/Cur and the 128-row waterfall ring."""
     d["Fft.Max"] = d["Fft.Min"] = d["Fft.Avg"] = d["Fft.Cur"] = None
+    d["kspec.state"] = None
     d["PltHeatMapWidth"] = heatmap_width(d["fftSize"], d["xRes"], d["pltCompressHM"])
     d["fftHM"] = np.zeros((HEATMAP_ROWS, d["PltHeatMapWidth"]))
     d["fftHMIndex"] = 0
+
+
+def _carried_state(d):
+    """(max, min, avg) carried from the earlier scans of this run, or None before the first one.  The GPU batch always
+    computes all three; bDataMax / bDataMin / bDataAvg (K:471-476) decide which of them reach d['Fft.*']."""
+    return d.get("kspec.state")
+
+
+def _publish_stats(d, out):
+    d["kspec.state"] = (out["max"], out["min"], out["avg"])
+    if d.get("bDataMax", True):
+        d["Fft.Max"] = out["max"]
+    if d.get("bDataMin", True):
+        d["Fft.Min"] = out["min"]
+    if d.get("bDataAvg", True):
+        d["Fft.Avg"] = out["avg"]
 
 
 def zero_span_block(d, samples, n_scans, rows="db"):
@@ -181,13 +198,11 @@ def zero_span_block(d, samples, n_scans, rows="db"):
     returns the batch dict (rows = Fft.Cur of every scan when rows == 'db')."""
     samples = np.ascontiguousarray(samples)
     plan = _plan(d, _ffi.in_format(samples))
-    state = None
-    if d.get("Fft.Max") is not None and d.get("Fft.Min") is not None and d.get("Fft.Avg") is not None:
-        state = (d["Fft.Max"], d["Fft.Min"], d["Fft.Avg"])
+    state = _carried_state(d)
     adj = d["Fft.Adj"] if d.get("AdjSigLvls", "") != "" else None
     out = plan.zerospan_batch(samples, n_scans, d["gain"], d["xRes"], d["pltCompressHM"], adj=adj, rows=rows,
                               want_hm=True, state=state)
-    d["Fft.Max"], d["Fft.Min"], d["Fft.Avg"] = out["max"], out["min"], out["avg"]
+    _publish_stats(d, out)
     if rows == "db":
         d["Fft.Cur"] = out["rows"][-1]
     for r in out["hm_rows"]:                                   # ring of 128 rows (K:480-484)
@@ -229,14 +244,12 @@ def zero_span_u8_file(d, path, block=256, save=None, clock=time.time):
     while done < n_total and not d["cmd.stop"]:
         n = min(block, n_total - done)
         chunk = np.ascontiguousarray(raw[2 * S * done:2 * S * (done + n)])
-        state = None
-        if d.get("Fft.Max") is not None:
-            state = (d["Fft.Max"], d["Fft.Min"], d["Fft.Avg"])
+        state = _carried_state(d)
         adj = d["Fft.Adj"] if d.get("AdjSigLvls", "") != "" else None
         t = clock()
         out = plan.zerospan_batch(chunk, n, d["gain"], d["xRes"], d["pltCompressHM"], adj=adj,
                                   rows="linear" if save is not None else "db", want_hm=True, state=state)
-        d["Fft.Max"], d["Fft.Min"], d["Fft.Avg"] = out["max"], out["min"], out["avg"]
+        _publish_stats(d, out)
         if save is not None:
             for row in out["rows"]:
                 pickle.dump(t, save)
@@ -323,12 +336,11 @@ def zero_span_play_all(d, block=64):
             recs.append(r)
         if not recs:
             break
-        state = None
-        if d.get("Fft.Max") is not None:
-            state = (d["Fft.Max"], d["Fft.Min"], d["Fft.Avg"])
+        state = _carried_state(d)
         adj = d["Fft.Adj"] if d.get("AdjSigLvls", "") != "" else None
         out = _plan(d).zerospan_rows_batch(np.array(recs), d["gain"], d["xRes"], d["pltCompressHM"], adj=adj, state=state)
-        d["Fft.Max"], d["Fft.Min"], d["Fft.Avg"], d["Fft.Cur"] = out["max"], out["min"], out["avg"], out["rows"][-1]
+        _publish_stats(d, out)
+        d["Fft.Cur"] = out["rows"][-1]
         for r in out["hm_rows"]:
             d["fftHM"][d["fftHMIndex"], :] = r
             d["fftHMIndex"] = (d["fftHMIndex"] + 1) % HEATMAP_ROWS
@@ -394,7 +406,10 @@ def _scan_range(d, freqsAll, fftAll, runCount=-1, reopen=None):
         else:
             print("WARN:_scanRange: Dummy data for step {}".format(i))
             ok[i] = 0
-    state = dict(cur=d["Fft.Cur"], max=d["Fft.Max"], min=d["Fft.Min"], avg=d["Fft.Avg"])
+    # bDataMax / bDataMin gate the Max / Min update (K:663-666; Avg is always updated, K:667): a disabled curve keeps its
+    # values because the batch works on a scratch copy of it
+    state = dict(cur=d["Fft.Cur"], max=d["Fft.Max"] if d.get("bDataMax", True) else d["Fft.Max"].copy(),
+                 min=d["Fft.Min"] if d.get("bDataMin", True) else d["Fft.Min"].copy(), avg=d["Fft.Avg"])
     _plan(d).scan_batch(samples, len(steps), [s[1] for s in steps], [s[2] for s in steps], totalEntries, d["minAmp4Clip"],
                         d["gain"], state, 0 if runCount == 0 else 1, step_ok=ok, base_is_raw=d["bScanRangeBaseDataIsRaw"])
     fftAvg = d["Fft.Avg"] - d["Fft.Adj"] if d.get("AdjSigLvls", "") != "" else d["Fft.Avg"]

@@ -53,3 +53,13 @@ def stitch_partial(db_rows, step_base, i_start, fft_size, total):
         sh = np.where(i == i0[b], i1[b] - i0[b], i1[b] - i + 1)
         out[b] += np.ldexp(np.asarray(row, dtype=np.float64)[:len(b)], -sh.astype(np.int64))
     return out
+
+
+def keep_uncovered(cur_sum, cur_prev, i_start, fft_size):
+    """after the SUM over shards of kspec_scan_shard's partials: bins that no step covers keep the previous Fft.Cur, as the
+    single-plan stitch does (K:643-650 never touches them); none exist in the reference's own geometries (K:598-600)"""
+    i0, i1 = scan_cover(i_start, fft_size, len(cur_sum))
+    unc = (i1 < 0) | (i0 > i1)
+    out = np.array(cur_sum, dtype=np.float64, copy=True)
+    out[unc] = np.asarray(cur_prev, dtype=np.float64)[unc]
+    return out

@@ -15,10 +15,11 @@ pytestmark = pytest.mark.gpu
 
 DB_TOL = 1e-3            # dB, the north-star tolerance
 F64_TOL = 1e-8           # dB, what the float64 engines actually deliver
-# float32 engines: rounding noise sits ~1e-8 of the strongest bin of the frame (measured), so the 1e-3 dB bar is
-# guaranteed for bins down to 1e-4 of the scan's peak (-40 dB in this program's 10*log10 convention, -80 dB in 20*log10);
-# weaker bins are held to an absolute error of 2e-7 of the peak instead.  precision "auto"/"f64" has no such limit.
-F32_DYN = 1e-4
+# float32 engines, the contract of include/kspec.h (KSPEC_PREC_F32): every bin within F32_ABS of the scan's strongest bin
+# (absolute, linear), hence within 1e-3 dB for the bins above F32_DYN of that peak; weaker bins carry no dB guarantee.
+# precision "auto"/"f64" has no such limit: 1e-8 dB on every bin.
+F32_ABS = 3e-7
+F32_DYN = 2e-3
 FS = 2.4e6
 
 
@@ -32,8 +33,8 @@ def assert_db_close(got_lin, ref_lin, tol=DB_TOL, what="", f32=False):
     floor = O.MIN_AMP4CLIP
     if f32:
         peak = float(ref_lin.max())
-        floor = max(floor, F32_DYN * peak * (1.0 if len(ref_lin) <= 4096 else 3.0))     # rounding noise grows ~sqrt(log2 F)
-        assert float(np.max(np.abs(got_lin - ref_lin))) < 2e-7 * peak, what
+        floor = max(floor, F32_DYN * peak)
+        assert float(np.max(np.abs(got_lin - ref_lin))) < F32_ABS * peak, what
     m = ref_lin > floor
     err = np.abs(db(got_lin[m]) - db(ref_lin[m]))
     assert err.size and float(err.max()) < tol, "%s max |dB err| %.3g at %d" % (what, err.max(), int(np.argmax(err)))
@@ -313,8 +314,8 @@ def test_r32_layout_ragged(fmt, cumu, r, wname):
     rl = np.asarray(ref_lin[3:])
     # the float32 contract (include/kspec.h, KSPEC_PREC_F32): every bin within 3e-7 of the scan's peak, hence within 1e-3 dB
     # wherever the bin is above 2e-3 of the peak; argmax bit-exact
-    assert np.max(np.abs(lin["rows"] - rl)) < 3e-7 * rl.max()
-    m = rl > 2e-3 * rl.max(axis=1, keepdims=True)
+    assert np.max(np.abs(lin["rows"] - rl)) < F32_ABS * rl.max()
+    m = rl > F32_DYN * rl.max(axis=1, keepdims=True)
     assert m.any() and np.max(np.abs(got["rows"][m] - ref["cur_rows"][3:][m])) < DB_TOL
     assert np.array_equal(np.argmax(got["rows"], axis=1), np.argmax(ref["cur_rows"][3:], axis=1))
     assert np.max(np.abs(got["max"] - ref["max"])) < (DB_TOL if cumu != "MIN" else 0.05)
@@ -755,8 +756,9 @@ def test_pipelined_host_batch_equals_single_shot(prec, shard, monkeypatch):
         kw.update(state=state)
     with Plan(F, S, r, win, "AVG", _ffi.IN_C64, precision=prec) as plan:
         one = plan.zerospan_batch(x, n, 19.1, 128, "MAX", **kw)
+    monkeypatch.setenv("KSPEC_PIPELINE_CHUNK_BYTES", str(64 * S * 8))      # read once, at plan creation
+    with Plan(F, S, r, win, "AVG", _ffi.IN_C64, precision=prec) as plan:
         launches0 = plan.launch_count()
-        monkeypatch.setenv("KSPEC_PIPELINE_CHUNK_BYTES", str(64 * S * 8))
         piped = plan.zerospan_batch(x, n, 19.1, 128, "MAX", **kw)
         assert plan.launch_count() - launches0 >= 5 * 2            # five parts: engine + stats each
     # the 64-scan parts take the frame-parallel form of the kernel, the one-shot batch the batch form: same values up to the
@@ -769,3 +771,125 @@ def test_pipelined_host_batch_equals_single_shot(prec, shard, monkeypatch):
         ref = O.zerospan(lin, 19.1, 128, "MAX", adj=adj, state=state)
         for k, kk in (("rows", "cur_rows"), ("hm_rows", "hm_rows"), ("max", "max"), ("min", "min"), ("avg", "avg")):
             assert np.max(np.abs(piped[k] - ref[kk])) < F64_TOL, k
+
+
+@pytest.mark.parametrize("fmt", ["u8", "c64"])
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_pipelined_host_batch_with_odd_full_size(fmt, prec, monkeypatch):
+    """an odd fullSize makes a scan a non-multiple of 16 bytes: the chunks of the pipelined host path must still start on
+    16-byte boundaries of the device buffer (the fused kernels stage frames with 16-byte granular bulk copies), and the
+    device entry point must refuse a misaligned sample pointer instead of faulting"""
+    F, S, r, n = 512, 4099, 0.3, 203
+    win = O.window_table("hamming", F)
+    x = synth.tones_noise(n * S, seed=78, dtype=np.complex128)
+    raw = synth.to_u8_iq(x) if fmt == "u8" else x.astype(np.complex64)
+    xin = synth.from_u8_iq(raw) if fmt == "u8" else raw.astype(np.complex128)
+    eb = 2 if fmt == "u8" else 8
+    monkeypatch.setenv("KSPEC_PIPELINE_CHUNK_BYTES", str(65 * S * eb))     # 65 scans: not a whole number of 16-byte granules
+    with Plan(F, S, r, win, "AVG", _ffi.in_format(raw), precision=prec) as plan:
+        got = plan.zerospan_batch(raw, n, 19.1, 128, "MAX", rows="linear")
+        import ctypes as C
+        from kspec._ffi import KspecError
+        d = plan.dev_alloc(raw.nbytes + 64)
+        plan.dev_upload(d, raw, offset=8)
+        with pytest.raises(KspecError):
+            plan.zerospan_batch_dev(C.c_void_p(d.value + 8), n, 19.1, 128, "MAX")
+        plan.dev_free(d)
+    ref = np.array([O.curscan(xin[k * S:(k + 1) * S], F, r, win, "AVG") for k in range(n)])
+    for k in range(n):
+        assert_db_close(got["rows"][k], ref[k], DB_TOL if prec == "f32" else F64_TOL, "scan %d" % k, f32=prec == "f32")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the float32 contract of include/kspec.h on the synthetic inputs of every BASELINE configuration
+# ---------------------------------------------------------------------------------------------------------------
+def _contract_rows(F, r, wname, cumu, x, S, n):
+    win = O.window_table(wname, F)
+    with Plan(F, S, r, win, cumu, _ffi.in_format(x), precision="f32") as plan:
+        offs = plan.frame_offsets()
+        got = plan.zerospan_batch(x, n, 19.1, 512, "MAX", rows="linear", want_hm=False)["rows"]
+    ref = np.array([O.curscan(x[k * S:(k + 1) * S].astype(np.complex128), F, r, win, cumu) for k in range(n)])
+    return got, ref, offs
+
+
+@pytest.mark.parametrize("cfg", ["cfg1", "cfg2", "cfg3", "cfg5a"])
+def test_f32_contract(cfg):
+    """KSPEC_PREC_F32 (include/kspec.h): every bin within 3e-7 of the scan's peak, bins above 2e-3 of the peak within 1e-3 dB,
+    argmax and frame offsets exact -- on the BASELINE synthetic input of every configuration where float32 can be selected;
+    on cfg 1 (the benchmark workload) every bin of every scan within 1e-3 dB."""
+    if cfg == "cfg1":
+        F, r, wname, cumu, n = 2048, 0.5, "hanning", "AVG", 146
+        S = O.full_size(F, FS)
+        x = synth.tones_noise(n * S, seed=1)
+    elif cfg == "cfg2":
+        F, r, wname, cumu, n = 64, 0.1, "ones", "AVG", 613
+        S = O.full_size(F, FS)
+        x = np.concatenate([synth.step_tones(s, S) for s in range(n)])
+    elif cfg == "cfg3":
+        F, r, wname, cumu, n = 8192, 0.25, "kaiser", "AVG", 40
+        S = O.full_size(F, FS)
+        x = synth.tones_noise(n * S, seed=3, gate=(40000, 0.5))
+    else:
+        F, r, wname, cumu, n = 4096, 0.1, "ones", "AVG", 18
+        S = O.full_size(F, FS)
+        x = np.concatenate([synth.step_tones(s, S) for s in range(n)])
+    got, ref, offs = _contract_rows(F, r, wname, cumu, x, S, n)
+    assert np.array_equal(offs, O.frame_offsets(F, S, r))
+    peak = ref.max(axis=1, keepdims=True)
+    assert np.max(np.abs(got - ref) / peak) < F32_ABS
+    m = ref > F32_DYN * peak
+    assert np.max(np.abs(db(got[m]) - db(ref[m]))) < DB_TOL
+    assert np.array_equal(np.argmax(got, axis=1), np.argmax(ref, axis=1))
+    if cfg == "cfg1":
+        assert np.max(np.abs(db(got) - db(ref))) < DB_TOL
+
+
+@pytest.mark.parametrize("F", [1 << 21, 2400000])
+def test_f32_is_refused_where_it_is_not_offered(F):
+    """cfg 4 (2^21) and cfg 5b (2.4e6) run on the multi-pass float64 engines: an explicit float32 request fails loudly"""
+    from kspec._ffi import KspecError
+    with pytest.raises(KspecError):
+        Plan(F, 2 * F, 0.1, np.ones(F), "MAX", _ffi.IN_C64, precision="f32")
+    with Plan(F, 2 * F, 0.1, np.ones(F), "MAX", _ffi.IN_C64, precision="auto") as plan:
+        assert plan.precision == "f64"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# memory safety of the staged bulk copies (compute-sanitizer is closed on this pool): poisoned guard regions
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fmt,prec,F,r,n", [
+    ("c64", "f32", 2048, 0.1, 37), ("u8", "f32", 2048, 0.1, 37), ("c64", "f32", 2048, 0.5, 1813), ("u8", "f32", 2048, 0.5, 1813),
+    ("c64", "f64", 2048, 0.1, 9), ("u8", "f64", 1024, 0.1, 9), ("c64", "f32", 256, 0.1, 300), ("c64", "f32", 8192, 0.25, 5),
+])
+def test_sample_buffer_between_poisoned_guards(fmt, prec, F, r, n):
+    """The sample batch sits flush between two guard regions filled with 0xFF bytes (NaN as float32, 255 as uint8).  The
+    16-byte granular bulk copies of the fused kernels (odd frame offsets at r = 0.1, the last frame of the last scan) must not
+    bring a guard byte into any result, and nothing may write outside the plan's own buffers: outputs identical to a run on a
+    zero-padded copy, guards unchanged."""
+    G = 4096
+    S = O.full_size(F, FS)
+    x = synth.tones_noise(n * S, seed=41, dtype=np.complex128)
+    raw = synth.to_u8_iq(x) if fmt == "u8" else x.astype(np.complex64)
+    nbytes = raw.nbytes
+    assert nbytes % 16 == 0
+    win = O.window_table("hanning", F)
+    with Plan(F, S, r, win, "AVG", _ffi.in_format(raw), precision=prec) as plan:
+        import ctypes as C
+        buf = plan.dev_alloc(nbytes + 2 * G)
+        poison = np.full(nbytes + 2 * G, 0xFF, dtype=np.uint8)
+        plan.dev_upload(buf, poison)
+        plan.dev_upload(buf, raw, offset=G)
+        plan.zerospan_batch_dev(C.c_void_p(buf.value + G), n, 19.1, 512, "MAX", rows="db")
+        a = plan.zerospan_fetch()
+        lo = plan.dev_download(buf, G)
+        hi = plan.dev_download(buf, G, offset=G + nbytes)
+        mid = plan.dev_download(buf, nbytes, offset=G)
+        plan.dev_upload(buf, np.zeros(nbytes + 2 * G, dtype=np.uint8))
+        plan.dev_upload(buf, raw, offset=G)
+        plan.zerospan_batch_dev(C.c_void_p(buf.value + G), n, 19.1, 512, "MAX", rows="db")
+        b = plan.zerospan_fetch()
+        plan.dev_free(buf)
+    assert (lo == 0xFF).all() and (hi == 0xFF).all() and np.array_equal(mid, raw.view(np.uint8).reshape(-1))
+    for k in ("rows", "hm_rows", "max", "min", "avg"):
+        assert np.isfinite(a[k]).all(), k
+        assert np.array_equal(a[k], b[k]), k

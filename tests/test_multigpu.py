@@ -46,7 +46,23 @@ def _worker(rank, world, uid_path, q):
         comm.allreduce_plan_stats(plan)
         comm.join(plan)
         dev = plan.zerospan_fetch()
+        # overlapped order: batch k, all-reduce (asynchronous), batch k+1 -> join must refuse (the plan now holds batch k+1),
+        # the reduced vectors of batch k come from fetch_reduced, the plan's own statistics are those of batch k+1
+        plan.zerospan_batch_dev(d, b - a, GAIN, XRES, "MAX", scan_index_base=a, n_scans_total=N)
+        comm.allreduce_plan_stats(plan)
+        half = (b - a) // 2
+        plan.zerospan_batch_dev(d, half, GAIN, XRES, "MAX")
+        from kspec._ffi import KspecError
+        try:
+            comm.join(plan)
+            refused = False
+        except KspecError:
+            refused = True
+        red = comm.fetch_reduced(F)
+        nxt = plan.zerospan_fetch()
         plan.dev_free(d)
+        local_half = plan.zerospan_batch(x[a * S:(a + half) * S], half, GAIN, XRES, "MAX")
+        overl_ok = bool(refused and np.array_equal(nxt["max"], local_half["max"]) and np.array_equal(nxt["avg"], local_half["avg"]))
     # stepped scan sharded by frequency step: SUM of the stitch partials over NVLink
     from oracle import kspec_oracle as O
     Fs, rs = 64, 0.1
@@ -62,7 +78,8 @@ def _worker(rank, world, uid_path, q):
         st = O.scan_init_state(total, 19.1)
         plan.scan_stats_update(cur, steps[-1]["i_done"], 0, st)
     comm.close()
-    q.put((rank, out["max"], out["min"], out["avg"], dev["max"], dev["min"], dev["avg"], st["cur"], st["max"], st["avg"]))
+    q.put((rank, out["max"], out["min"], out["avg"], dev["max"], dev["min"], dev["avg"], st["cur"], st["max"], st["avg"],
+           red[0], red[1], red[2], overl_ok))
 
 
 @pytest.mark.skipif(device_count() < 2, reason="needs two GPUs")
@@ -90,7 +107,8 @@ def test_two_gpu_shards_match_single_gpu(tmp_path):
     lin = [O.curscan(synth.step_tones(s, 512).astype(np.complex128), 64, 0.1, np.ones(64)) for s in range(len(steps))]
     sref = O.scan_pass(lin, [True] * len(steps), geo, 19.1, O.scan_init_state(total, 19.1), 0)
     for r in res:
-        for got in (r[1:4], r[4:7]):
+        assert r[13], "overlapped order: join must refuse and leave the plan's batch k+1 statistics alone"
+        for got in (r[1:4], r[4:7], r[10:13]):
             assert np.array_equal(got[0], ref["max"]) and np.array_equal(got[1], ref["min"])
             assert np.max(np.abs(got[2] - ref["avg"])) < 1e-9
         assert np.max(np.abs(r[7] - sref["cur"])) < 1e-9 and np.max(np.abs(r[8] - sref["max"])) < 1e-9
