@@ -16,8 +16,14 @@ Max/Min/Avg vectors are all-reduced (NCCL).
   roofline  HBM: algorithmic bytes per launch of the fused scan kernel / its measured duration / measured HBM peak
   cpu_baseline  the oracle port (numpy float64, the reference's algorithm) on the host cores, bounded sample
 
---impl reference times the reference algorithm (oracle port; the Python reference itself cannot travel to the GPU
-box) on all host cores for the same metric/config.
+  value_f64 / roofline_f64  the same device-resident step in KSPEC_PREC_AUTO (= float64: 1e-8 dB on every bin), fewer steps
+  parity_check  (N > 1, outside the timed region) a cfg-3 shaped capture (fftSize 8192, kaiser, 75 % overlap, float64)
+          sharded by scan range over the ranks + NCCL MAX/MIN/SUM against ONE plan over the whole capture on rank 0:
+          Max/Min bit-exact, Avg <= 1e-9 dB; the run exits non-zero if it fails
+
+--impl reference times the reference's own CPU implementation on all host cores for the same metric/config: the unmodified
+kspecanal.py functions when /root/reference is present (build container), else the oracle port (the Python reference cannot
+travel to the GPU box); cpu_baseline.kind says which.
 """
 import argparse
 import json
@@ -185,12 +191,57 @@ def algorithmic_bytes(n_scans):
 # CPU: the reference algorithm (oracle port) on host cores
 # ---------------------------------------------------------------------------------------------------------------
 CPU_BLOCK = 64      # scans synthesised per process; the timed loop walks this block repeatedly
+CPU_WHAT = {"reference": "the unmodified kspecanal.py functions (sdr_curscan, fftvals_dispproc, data_cumu x3, _data_plotcompress) loaded from /root/reference",
+            "port": "numpy float64 oracle port of kspecanal.py:351-397,464-484 (no /root/reference on this host)"}
+
+
+def cpu_kind():
+    from oracle import ref_loader
+    return "reference" if ref_loader.available() else "port"
+
+
+def _cpu_worker_reference(seed, n_scans):
+    """the UNMODIFIED kspecanal.py loop body (K:464-480) on its own numpy sdr_curscan: build container only"""
+    import contextlib
+    import io
+    from kspec import synth
+    from oracle import ref_loader
+    ns = ref_loader.load()
+    with contextlib.redirect_stdout(io.StringIO()):
+        d = ref_loader.base_dict(ns, ["zeroSpan", "fftSize", F, "window", "hanning", "curScanNonOverlap", R_NONOVERLAP, "xRes", XRES])
+    d["Fft.Max"] = d["Fft.Min"] = d["Fft.Avg"] = None
+    x = synth.tones_noise(CPU_BLOCK * S, seed=seed).astype(np.complex128)
+
+    class LoopSdr:                                   # read_samples(n) walks the 64-scan block again and again (K:339-346)
+        pos = 0
+
+        def read_samples(self, n):
+            n = int(n)
+            if self.pos + n > len(x):
+                self.pos = 0
+            out = x[self.pos:self.pos + n]
+            self.pos += n
+            return out
+
+    d["sdr"] = LoopSdr()
+    cumu, dispproc, compress, curscan = ns["data_cumu"], ns["fftvals_dispproc"], ns["_data_plotcompress"], ns["sdr_curscan"]
+    t0 = time.perf_counter()
+    for _ in range(n_scans):
+        lin = curscan(d)
+        pr = dispproc(d, lin, "LogNoGain")
+        d["Fft.Max"] = cumu(d, "MAX", d["Fft.Max"], 0, len(pr), pr, 0, len(pr))
+        d["Fft.Min"] = cumu(d, "MIN", d["Fft.Min"], 0, len(pr), pr, 0, len(pr))
+        d["Fft.Avg"] = cumu(d, "AVG", d["Fft.Avg"], 0, len(pr), pr, 0, len(pr))
+        compress(d, pr, "MAX")
+    return time.perf_counter() - t0
 
 
 def _cpu_worker(args):
     seed, n_scans = args
     from kspec import synth
     from oracle import kspec_oracle as O
+    if cpu_kind() == "reference":
+        return _cpu_worker_reference(seed, n_scans)
     win = O.window_table("hanning", F)
     x = synth.tones_noise(CPU_BLOCK * S, seed=seed).astype(np.complex128)    # the reference's dtype (K:335)
     t0 = time.perf_counter()
@@ -240,8 +291,8 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / max(args.steps, 1) * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": "%d processes x %d scans of the same configuration per step" % (procs, scans)},
-        "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": procs, "kind": "port",
-                         "sample": "%d scans (%d IQ samples) per step, numpy float64 oracle port of kspecanal.py:351-397,464-484" % (procs * scans, procs * scans * S)},
+        "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": procs, "kind": cpu_kind(),
+                         "sample": "%d scans (%d IQ samples) per step, %s" % (procs * scans, procs * scans * S, CPU_WHAT[cpu_kind()])},
         "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -252,6 +303,15 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------------
 # GPU
 # ---------------------------------------------------------------------------------------------------------------
+def mark(msg):
+    """progress marker on stderr (KSPEC_BENCH_VERBOSE=1): where a multi-rank run is when something stalls"""
+    if os.environ.get("KSPEC_BENCH_VERBOSE"):
+        print("[bench rank %s %.1fs] %s" % (os.environ.get("RANK", "0"), time.perf_counter() - T_START, msg), file=sys.stderr, flush=True)
+
+
+T_START = time.perf_counter()
+
+
 def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -291,6 +351,12 @@ def run_ours(args):
         comm = _make_comm(world, rank, local, dist)
         plan.reserve_sms(int(os.environ.get("KSPEC_SM_RESERVE", "0")))      # measured: reserving SMs for the NCCL kernels does not pay (profiles/README.md)
     comm_sync = bool(int(os.environ.get("KSPEC_COMM_SYNC", "0")))
+    mark("buffers ready")
+    parity = None
+    if comm is not None and not os.environ.get("KSPEC_BENCH_FAST"):
+        parity = parity_check(world, rank, local, comm)
+        mark("parity check done")
+        dist.barrier()
     total_scans = N_SCANS * world
     base_idx = rank * N_SCANS
 
@@ -315,6 +381,7 @@ def run_ours(args):
         return out
 
     # ---- device-resident timing -----------------------------------------------------------------------------
+    mark("device-resident timing")
     sampler = ClockSampler(local)
     sampler.start()
     for _ in range(args.warmup):
@@ -331,9 +398,9 @@ def run_ours(args):
     t_region1 = time.perf_counter()
     launches = plan.launch_count() - l0
     kt = plan.kernel_times(min(args.steps, 64))
-    # keep the identical load running (untimed) until the clock sampler has seen it for long enough
-    t_load = time.perf_counter()
-    while len(sampler.rows) < 25 and time.perf_counter() - t_load < 1.0:
+    # keep the identical load running (untimed) so that the clock sampler sees it for long enough.  A FIXED number of steps:
+    # every step is a collective at N > 1, so all ranks must issue the same count
+    for _ in range(12):
         for _ in range(8):
             step_dev()
         plan.sync()
@@ -351,6 +418,9 @@ def run_ours(args):
                               "kernel_ms": k_ms, "frac": algorithmic_bytes(N_SCANS) / (k_ms * 1e-3) / 1e9 / peaks()[0],
                               "ctas_per_sm": info.ctas_per_sm, "smem": info.smem_bytes, "stages": info.tma_stages, "clocks": clocks}))
         return 0
+    mark("float64 leg")
+    f64 = f64_leg(plan, d_samples, local, world, dist, min(args.steps, 5))
+    mark("end-to-end leg")
     # ---- end to end -----------------------------------------------------------------------------------------------
     step_e2e()
     barrier()
@@ -373,6 +443,7 @@ def run_ours(args):
         except Exception as exc:                                    # never let the extra leg cost the headline line
             e2e_u8 = {"error": str(exc)[:200]}
 
+    mark("cpu baseline (rank 0)")
     if rank == 0:
         peak, peak_src = peaks()
         k_ms = float(np.mean(kt)) if kt else ms / args.steps
@@ -394,21 +465,98 @@ def run_ours(args):
                        "cta_threads": info.cta_threads, "ctas_per_sm": info.ctas_per_sm, "smem_bytes": info.smem_bytes},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": profiled_traffic()[0], "traffic_source": profiled_traffic()[1], "other_pipes": profiled_pipes(),
-                         "peak_source": peak_src, "kernel": "curscan_smem_kernel<%s,C64,11>" % ("float" if plan.precision == "f32" else "double"), "kernel_ms": k_ms,
+                         "peak_source": peak_src, "kernel": ("curscan_r32_kernel<C64>" if plan.precision == "f32" else "curscan_smem_kernel<double,C64,11>"), "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": algorithmic_bytes(N_SCANS)},
-            "cpu_baseline": {"value": cpu_v, "unit": "Msamples/s", "cores": cores, "kind": "port", "single_core_value": cpu_1,
-                             "sample": "%d scans per process x %d processes (%.0f M IQ samples), best of 2, numpy float64 oracle port" % (640, cores, 640 * cores * S / 1e6)},
+            "cpu_baseline": {"value": cpu_v, "unit": "Msamples/s", "cores": cores, "kind": cpu_kind(), "single_core_value": cpu_1,
+                             "sample": "%d scans per process x %d processes (%.0f M IQ samples), best of 2, %s" % (640, cores, 640 * cores * S / 1e6, CPU_WHAT[cpu_kind()])},
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "e2e_uint8_iq": e2e_u8,
+            "value_f64": f64["value"], "roofline_f64": f64["roofline"], "f64": f64,
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        if parity is not None:
+            line["parity_check"] = parity
         print(json.dumps(line))
+        if parity is not None and not parity["ok"]:
+            sys.stdout.flush()
+            os._exit(3)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     plan.dev_free(d_samples)
     plan.close()
     return 0
+
+
+def parity_check(world, rank, local, comm):
+    """N > 1, outside every timed region: BASELINE cfg-3 shape (fftSize 8192, kaiser(64), 75 % overlap, float64), 96 scans
+    per rank sharded by scan range.  Every rank runs its shard (host path + NCCL on host vectors, then device-resident path
+    + asynchronous NCCL on the plan's vectors); rank 0 also runs ONE plan over the whole capture.  K:460-476."""
+    from kspec import _ffi, synth
+    from kspec.engine import Plan
+    # 96 scans per rank: above the 64-scan limit of the frame-parallel small-batch form, so that the shards and the single plan
+    # run the same kernel form and the comparison can be bit-exact
+    F3, r3, per = 8192, 0.25, 96
+    S3, n = F3 * 8, per * world
+    x = synth.tones_noise(n * S3, seed=3, gate=(40000, 0.5))           # seeded: every rank builds the same capture
+    win = np.kaiser(F3, 64)
+    a = rank * per
+    shard = x[a * S3:(a + per) * S3]
+    with Plan(F3, S3, r3, win, "AVG", _ffi.IN_C64, precision="f64", device=local) as plan:
+        mark("parity: capture built")
+        out = plan.zerospan_batch(shard, per, GAIN, XRES, "MAX", scan_index_base=a, n_scans_total=n)
+        comm.allreduce_host(out["max"], out["min"], out["avg"])
+        mark("parity: host all-reduce done")
+        d = plan.dev_alloc(shard.nbytes)
+        plan.dev_upload(d, shard)
+        plan.zerospan_batch_dev(d, per, GAIN, XRES, "MAX", scan_index_base=a, n_scans_total=n)
+        comm.allreduce_plan_stats(plan)
+        comm.join(plan)
+        dev = plan.zerospan_fetch(rows=False, hm=False)
+        mark("parity: device all-reduce done")
+        plan.dev_free(d)
+        if rank != 0:
+            return None
+        one = plan.zerospan_batch(x, n, GAIN, XRES, "MAX")
+    err = {}
+    ok = True
+    for name, got in (("host_allreduce", out), ("device_allreduce", dev)):
+        e = {k: float(np.max(np.abs(got[k] - one[k]))) for k in ("max", "min", "avg")}
+        ok = ok and np.array_equal(got["max"], one["max"]) and np.array_equal(got["min"], one["min"]) and e["avg"] <= 1e-9
+        err[name] = e
+    return {"n_ranks": world, "shape": "fftSize 8192 kaiser 75 %% overlap float64, %d scans per rank, sharded by scan range" % per,
+            "criterion": "Max/Min bit-exact, Avg <= 1e-9 dB against one plan over the whole capture", "max_abs_err": err,
+            "max_abs_err_all": max(max(e.values()) for e in err.values()), "ok": bool(ok)}
+
+
+def f64_leg(plan32, d_samples, local, world, dist, steps):
+    """the same device-resident step in the default precision (KSPEC_PREC_AUTO = float64)"""
+    from kspec import _ffi
+    from kspec.engine import Plan
+    plan32.sync()
+    with Plan(F, S, R_NONOVERLAP, np.hanning(F), "AVG", _ffi.IN_C64, precision="auto", device=local) as plan:
+        def step():
+            plan.zerospan_batch_dev(d_samples, N_SCANS, GAIN, XRES, "MAX", rows=None, want_hm=True)
+        for _ in range(3):
+            step()
+        plan.sync()
+        if dist is not None:
+            dist.barrier()
+        plan.timer_start()
+        for _ in range(steps):
+            step()
+        ms = plan.timer_stop()
+        kt = plan.kernel_times(min(steps, 64))
+        info = plan.info
+    ms_all = _max_over_ranks(ms, dist, local)
+    k_ms = float(np.mean(kt)) if kt else ms / steps
+    alg = N_SCANS * S * 8 + N_SCANS * XRES * 8 + 4 * F * 8            # float64 outputs are 8 bytes each
+    peak, peak_src = peaks()
+    return {"value": world * N_SCANS * S * steps / (ms_all * 1e-3) / 1e6, "unit": "Msamples/s", "steps": steps, "ms_per_step": ms_all / steps,
+            "dtype": "f64", "cta_threads": info.cta_threads, "ctas_per_sm": info.ctas_per_sm,
+            "roofline": {"bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (k_ms * 1e-3) / 1e9 / peak, "kernel": "curscan_smem_kernel<double,C64,11>", "kernel_ms": k_ms,
+                         "algorithmic_bytes_per_launch": alg, "peak_source": peak_src}}
 
 
 def e2e_uint8_leg(win, S, host_out, steps):
