@@ -141,6 +141,21 @@ int kspec_scan_batch(kspec_plan* plan, const void* samples, int nSteps, const ui
                      double minAmp4Clip, double gain, int baseIsRaw, int passIndex,
                      double* cur, double* max, double* min, double* avg);
 
+/* ---- the same pass with Fft.Cur/Max/Min/Avg RESIDENT ON THE DEVICE across passes (K:602-668; scan_range's loop K:719-732) -----
+ * kspec_scan_batch moves four totalEntries-long float64 vectors to the device and back on every pass (21.6 M entries at
+ * fftSize 2.4e6: 691 MB each way).  Here the state lives in the plan: kspec_scan_state_init uploads it once (the host
+ * initialises it per K:602-608), kspec_scan_pass runs one pass -- the steps' samples cross PCIe in chunks on a copy stream
+ * while the engine transforms the chunks that have arrived, then one stitch + Max/Min/Avg kernel updates the state in HBM --
+ * and kspec_scan_state_fetch copies out whichever vectors the host wants to look at (NULL = skip).  kspec_scan_pass_dev
+ * takes samples that are already on the device (16-byte aligned).  Arguments as in kspec_scan_batch. */
+int kspec_scan_state_init(kspec_plan* plan, int64_t totalEntries, const double* cur, const double* max, const double* min,
+                          const double* avg);
+int kspec_scan_pass(kspec_plan* plan, const void* samples, int nSteps, const uint8_t* stepOk, const int64_t* iStart,
+                    const int64_t* iDone, double minAmp4Clip, double gain, int baseIsRaw, int passIndex);
+int kspec_scan_pass_dev(kspec_plan* plan, const void* d_samples, int nSteps, const uint8_t* stepOk, const int64_t* iStart,
+                        const int64_t* iDone, double minAmp4Clip, double gain, int baseIsRaw, int passIndex);
+int kspec_scan_state_fetch(kspec_plan* plan, double* cur, double* max, double* min, double* avg);
+
 /* ---- the same pass sharded by frequency step over several plans / GPUs -----------------------------------
  * kspec_scan_shard: this plan holds the captures of steps [stepBase, stepBase+nStepsLocal) of nStepsTotal; iStart has
  * nStepsTotal entries (the global geometry).  curPartial (totalEntries) receives this shard's share of the stitched

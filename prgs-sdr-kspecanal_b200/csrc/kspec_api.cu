@@ -89,7 +89,8 @@ struct kspec_plan {
     void* dTw = nullptr;
     void* dTwLin = nullptr;
     // grow-only workspaces
-    DevBuf in, rows, hm, wsMax, wsMin, avgRows, adj, adj64, carry, stats, wide, acc, l2, misc, frameRows, vbase;
+    DevBuf in, rows, hm, wsMax, wsMin, avgRows, adj, adj64, carry, stats, wide, acc, l2, misc, frameRows, vbase, scanState, scanGeo;
+    int64_t scanTotal = 0;                         // entries of the device-resident stepped-scan state (0: none)
     int64_t vbaseScans = 0;                        // scans covered by the frame-parallel base table in vbase
     // what the last *_dev batch left behind (for fetch)
     int64_t lastScans = 0;
@@ -484,7 +485,7 @@ int kspec_plan_destroy(kspec_plan* pl) {
     if (pl->big) bigfft_destroy(pl->big);
     if (pl->mixed) mixedradix_destroy(pl->mixed);
     for (DevBuf* b : {&pl->in, &pl->rows, &pl->hm, &pl->wsMax, &pl->wsMin, &pl->avgRows, &pl->adj, &pl->adj64, &pl->carry, &pl->stats,
-                      &pl->wide, &pl->acc, &pl->l2, &pl->misc, &pl->frameRows, &pl->vbase}) b->release();
+                      &pl->wide, &pl->acc, &pl->l2, &pl->misc, &pl->frameRows, &pl->vbase, &pl->scanState, &pl->scanGeo}) b->release();
     if (pl->dOffs) cudaFree(pl->dOffs);
     if (pl->dWin) cudaFree(pl->dWin);
     if (pl->dTw) cudaFree(pl->dTw);
@@ -865,6 +866,144 @@ int kspec_scan_batch(kspec_plan* pl, const void* samples, int nSteps, const uint
     CK(cudaStreamSynchronize(pl->st));
     pl->haveBatch = false;
     return KSPEC_OK;
+}
+
+// ---- stepped scan with the state resident on the device (K:602-668 over many passes) -----------------------------------------
+namespace {
+
+int scan_geometry_check(const kspec_plan* pl, int nSteps, const int64_t* iStart, const int64_t* iDone) {
+    if (nSteps < 1 || !iStart || !iDone) { set_error("bad scan geometry"); return KSPEC_ERR_ARG; }
+    for (int i = 1; i < nSteps; ++i)
+        if (iStart[i] < iStart[i - 1] || iStart[i] > iStart[i - 1] + pl->F) { set_error("scanRangeNonOverlap must be in (0,1]: step %d starts at %lld after %lld", i, (long long)iStart[i], (long long)iStart[i - 1]); return KSPEC_ERR_ARG; }
+    return KSPEC_OK;
+}
+
+// one pass: engine over the steps (chunked and overlapped with the host->device copies when the samples are on the host),
+// then the stitch + Max/Min/Avg kernel on the device-resident state
+int scan_pass_common(kspec_plan* pl, const void* samples, bool onDevice, int nSteps, const uint8_t* stepOk, const int64_t* iStart,
+                     const int64_t* iDone, double minAmp4Clip, double gain, int baseIsRaw, int passIndex) {
+    if (check_plan(pl)) return KSPEC_ERR_ARG;
+    if (!samples) { set_error("no samples"); return KSPEC_ERR_ARG; }
+    if (pl->scanTotal < 1) { set_error("kspec_scan_pass before kspec_scan_state_init"); return KSPEC_ERR_STATE; }
+    int rc;
+    if ((rc = scan_geometry_check(pl, nSteps, iStart, iDone))) return rc;
+    DeviceGuard guard(pl->device);
+    const int F = pl->F;
+    const size_t rb = real_bytes(pl->prec);
+    const size_t stepBytes = (size_t)pl->S * in_elem_bytes(pl->inFmt);
+    if ((rc = pl->rows.reserve((size_t)nSteps * F * rb))) return rc;
+    // geometry
+    const size_t geoBytes = (size_t)nSteps * (8 + 8 + 1) + 64;
+    if ((rc = pl->scanGeo.reserve(geoBytes))) return rc;
+    int64_t* dStart = (int64_t*)pl->scanGeo.p;
+    int64_t* dDone = dStart + nSteps;
+    uint8_t* dOk = (uint8_t*)(dDone + nSteps);
+    CK(cudaMemcpyAsync(dStart, iStart, (size_t)nSteps * 8, cudaMemcpyHostToDevice, pl->st));
+    CK(cudaMemcpyAsync(dDone, iDone, (size_t)nSteps * 8, cudaMemcpyHostToDevice, pl->st));
+    if (stepOk) CK(cudaMemcpyAsync(dOk, stepOk, (size_t)nSteps, cudaMemcpyHostToDevice, pl->st));
+
+    auto engine = [&](const void* dSamples, int first, int count) -> int {
+        ScanParams p = base_params(pl, dSamples, count);
+        p.rowsKind = KSPEC_ROWS_DB;
+        p.rows = (char*)pl->rows.p + (size_t)first * F * rb;
+        p.dbClip = 1; p.minAmp = minAmp4Clip; p.infToZero = 1; p.gain = gain;
+        int slots = 0;
+        return run_engine(pl, p, &slots);
+    };
+    if (onDevice) {
+        if (pl->path == KSPEC_PATH_SMEM && ((uintptr_t)samples & 15) != 0) { set_error("device sample buffer must be 16-byte aligned"); return KSPEC_ERR_ARG; }
+        if ((rc = engine(samples, 0, nSteps))) return rc;
+    } else {
+        if ((rc = pl->in.reserve((size_t)nSteps * stepBytes + TAIL_PAD))) return rc;
+        // chunks of whole steps, each starting on a 16-byte boundary; at least four chunks when the pass is large enough to matter
+        int64_t chunkSteps = (int64_t)(((size_t)64 << 20) / stepBytes);
+        if (chunkSteps < 1) chunkSteps = 1;
+        if ((size_t)nSteps * stepBytes < ((size_t)8 << 20)) chunkSteps = nSteps;          // small pass: one copy
+        int64_t grp = 1;
+        while ((grp * (int64_t)stepBytes) % 16 != 0) grp *= 2;
+        chunkSteps = (chunkSteps + grp - 1) / grp * grp;
+        const int64_t nChunks = (nSteps + chunkSteps - 1) / chunkSteps;
+        if (nChunks == 1) {
+            CK(cudaMemcpyAsync(pl->in.p, samples, (size_t)nSteps * stepBytes, cudaMemcpyHostToDevice, pl->st));
+            if ((rc = engine(pl->in.p, 0, nSteps))) return rc;
+        } else {
+            if (!pl->stCopy) CK(cudaStreamCreateWithFlags(&pl->stCopy, cudaStreamNonBlocking));
+            while ((int64_t)pl->evChunk.size() < nChunks + 1) {
+                cudaEvent_t e;
+                CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                pl->evChunk.push_back(e);
+            }
+            CK(cudaEventRecord(pl->evChunk[nChunks], pl->st));          // the copy stream may not overwrite samples still in use
+            CK(cudaStreamWaitEvent(pl->stCopy, pl->evChunk[nChunks], 0));
+            for (int64_t c = 0; c < nChunks; ++c) {
+                const int64_t s0 = c * chunkSteps, ns = (nSteps - s0 < chunkSteps) ? nSteps - s0 : chunkSteps;
+                CK(cudaMemcpyAsync((char*)pl->in.p + (size_t)s0 * stepBytes, (const char*)samples + (size_t)s0 * stepBytes, (size_t)ns * stepBytes,
+                                   cudaMemcpyHostToDevice, pl->stCopy));
+                CK(cudaEventRecord(pl->evChunk[c], pl->stCopy));
+            }
+            for (int64_t c = 0; c < nChunks; ++c) {
+                const int64_t s0 = c * chunkSteps, ns = (nSteps - s0 < chunkSteps) ? nSteps - s0 : chunkSteps;
+                CK(cudaStreamWaitEvent(pl->st, pl->evChunk[c], 0));
+                if ((rc = engine((const char*)pl->in.p + (size_t)s0 * stepBytes, (int)s0, (int)ns))) return rc;
+            }
+        }
+    }
+    double one = 1.0 > minAmp4Clip ? 1.0 : minAmp4Clip;             // tune failure: ones(F) through clip + dB (K:637-641)
+    double failValue = 10.0 * log10(one) - gain;
+    if (isinf(failValue)) failValue = 0.0;
+    double* dCur = (double*)pl->scanState.p;
+    const int64_t T = pl->scanTotal;
+    launch_scan_stitch(pl->prec, pl->rows.p, stepOk ? dOk : nullptr, dStart, dDone, nSteps, F, T, failValue, baseIsRaw, passIndex,
+                       dCur, dCur + T, dCur + 2 * T, dCur + 3 * T, pl->st);
+    pl->launches += 1;
+    CK(cudaGetLastError());
+    if (!onDevice) CK(cudaStreamSynchronize(pl->st));               // the caller's sample buffer is free again
+    pl->haveBatch = false;
+    return KSPEC_OK;
+}
+
+}  // namespace
+
+int kspec_scan_state_init(kspec_plan* pl, int64_t totalEntries, const double* cur, const double* mx, const double* mn, const double* av) {
+    if (check_plan(pl)) return KSPEC_ERR_ARG;
+    if (totalEntries < 1 || !cur || !mx || !mn || !av) { set_error("bad scan state arguments"); return KSPEC_ERR_ARG; }
+    DeviceGuard guard(pl->device);
+    const size_t b = (size_t)totalEntries * 8;
+    int rc;
+    if ((rc = pl->scanState.reserve(4 * b))) return rc;
+    double* d = (double*)pl->scanState.p;
+    CK(cudaMemcpyAsync(d, cur, b, cudaMemcpyHostToDevice, pl->st));
+    CK(cudaMemcpyAsync(d + totalEntries, mx, b, cudaMemcpyHostToDevice, pl->st));
+    CK(cudaMemcpyAsync(d + 2 * totalEntries, mn, b, cudaMemcpyHostToDevice, pl->st));
+    CK(cudaMemcpyAsync(d + 3 * totalEntries, av, b, cudaMemcpyHostToDevice, pl->st));
+    CK(cudaStreamSynchronize(pl->st));
+    pl->scanTotal = totalEntries;
+    return KSPEC_OK;
+}
+
+int kspec_scan_state_fetch(kspec_plan* pl, double* cur, double* mx, double* mn, double* av) {
+    if (check_plan(pl)) return KSPEC_ERR_ARG;
+    if (pl->scanTotal < 1) { set_error("kspec_scan_state_fetch before kspec_scan_state_init"); return KSPEC_ERR_STATE; }
+    DeviceGuard guard(pl->device);
+    const int64_t T = pl->scanTotal;
+    const size_t b = (size_t)T * 8;
+    const double* d = (const double*)pl->scanState.p;
+    if (cur) CK(cudaMemcpyAsync(cur, d, b, cudaMemcpyDeviceToHost, pl->st));
+    if (mx) CK(cudaMemcpyAsync(mx, d + T, b, cudaMemcpyDeviceToHost, pl->st));
+    if (mn) CK(cudaMemcpyAsync(mn, d + 2 * T, b, cudaMemcpyDeviceToHost, pl->st));
+    if (av) CK(cudaMemcpyAsync(av, d + 3 * T, b, cudaMemcpyDeviceToHost, pl->st));
+    CK(cudaStreamSynchronize(pl->st));
+    return KSPEC_OK;
+}
+
+int kspec_scan_pass(kspec_plan* pl, const void* samples, int nSteps, const uint8_t* stepOk, const int64_t* iStart, const int64_t* iDone,
+                    double minAmp4Clip, double gain, int baseIsRaw, int passIndex) {
+    return scan_pass_common(pl, samples, false, nSteps, stepOk, iStart, iDone, minAmp4Clip, gain, baseIsRaw, passIndex);
+}
+
+int kspec_scan_pass_dev(kspec_plan* pl, const void* dSamples, int nSteps, const uint8_t* stepOk, const int64_t* iStart, const int64_t* iDone,
+                        double minAmp4Clip, double gain, int baseIsRaw, int passIndex) {
+    return scan_pass_common(pl, dSamples, true, nSteps, stepOk, iStart, iDone, minAmp4Clip, gain, baseIsRaw, passIndex);
 }
 
 // ---- stepped scan sharded by frequency step -----------------------------------------------------------------

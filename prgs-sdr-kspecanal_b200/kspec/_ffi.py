@@ -56,6 +56,10 @@ SIGNATURES = {
     "kspec_zerospan_rows_batch": (C.c_int, [_P, _D, _I64, C.c_double, _D, C.c_int, C.c_int, _D, _D, _D, _D, _D, C.c_int]),
     "kspec_scan_batch": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_uint8), C.POINTER(_I64), C.POINTER(_I64), _I64, C.c_double,
                                    C.c_double, C.c_int, C.c_int, _D, _D, _D, _D]),
+    "kspec_scan_state_init": (C.c_int, [_P, _I64, _D, _D, _D, _D]),
+    "kspec_scan_pass": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_uint8), C.POINTER(_I64), C.POINTER(_I64), C.c_double, C.c_double, C.c_int, C.c_int]),
+    "kspec_scan_pass_dev": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_uint8), C.POINTER(_I64), C.POINTER(_I64), C.c_double, C.c_double, C.c_int, C.c_int]),
+    "kspec_scan_state_fetch": (C.c_int, [_P, _D, _D, _D, _D]),
     "kspec_scan_shard": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint8), C.POINTER(_I64), _I64, C.c_double, C.c_double, _D]),
     "kspec_scan_stats_update": (C.c_int, [_P, _D, _I64, _I64, C.c_int, _D, _D, _D]),
     "kspec_plotcompress": (C.c_int, [_P, _D, _I64, C.c_int, C.c_int, _D]),

@@ -159,6 +159,35 @@ class Plan:
                                           dptr(state["cur"]), dptr(state["max"]), dptr(state["min"]), dptr(state["avg"])))
         return state
 
+    # -- the same pass with the state resident on the device (kspec_scan_state_* / kspec_scan_pass) ------------------------
+    def scan_state_init(self, state):
+        """state: dict(cur, max, min, avg) of float64[totalEntries] (K:602-608), uploaded once"""
+        a = {k: np.ascontiguousarray(state[k], dtype=np.float64) for k in ("cur", "max", "min", "avg")}
+        n = len(a["cur"])
+        check(_ffi.lib().kspec_scan_state_init(self._h, n, dptr(a["cur"]), dptr(a["max"]), dptr(a["min"]), dptr(a["avg"])))
+        self._scan_total = n
+
+    def scan_pass(self, samples, n_steps, i_start, i_done, min_amp, gain, pass_index, step_ok=None, base_is_raw=False, on_device=False):
+        """one pass of _scan_range on the device-resident state; samples: host array (chunked, overlapped H2D) or, with
+        on_device=True, a device pointer"""
+        i_start = np.ascontiguousarray(i_start, dtype=np.int64)
+        i_done = np.ascontiguousarray(i_done, dtype=np.int64)
+        ok = None if step_ok is None else np.ascontiguousarray(step_ok, dtype=np.uint8)
+        okp = None if ok is None else ok.ctypes.data_as(C.POINTER(C.c_uint8))
+        args = (int(n_steps), okp, i_start.ctypes.data_as(C.POINTER(C.c_int64)), i_done.ctypes.data_as(C.POINTER(C.c_int64)),
+                float(min_amp), float(gain), 1 if base_is_raw else 0, int(pass_index))
+        if on_device:
+            check(_ffi.lib().kspec_scan_pass_dev(self._h, samples, *args))
+        else:
+            a = self._samples(samples, n_steps)
+            check(_ffi.lib().kspec_scan_pass(self._h, vptr(a), *args))
+
+    def scan_state_fetch(self, which=("cur", "max", "min", "avg")):
+        n = self._scan_total
+        out = {k: (np.empty(n, dtype=np.float64) if k in which else None) for k in ("cur", "max", "min", "avg")}
+        check(_ffi.lib().kspec_scan_state_fetch(self._h, dptr(out["cur"]), dptr(out["max"]), dptr(out["min"]), dptr(out["avg"])))
+        return {k: v for k, v in out.items() if v is not None}
+
     # -- the same pass sharded by frequency step (SURVEY 8e) ---------------------------------------------------------
     def scan_shard(self, samples, n_local, step_base, i_start_all, total_entries, min_amp, gain, step_ok=None):
         """this shard's share of the stitched Fft.Cur (float64[totalEntries]); SUM over shards = Fft.Cur"""

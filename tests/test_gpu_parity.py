@@ -120,6 +120,71 @@ def test_scan_golden(name, prec, frame_parallel, monkeypatch):
     assert np.array_equal(np.argmax(st["cur"].reshape(-1, F), axis=1), np.argmax(g["p%d_cur" % (p["nPass"] - 1)].reshape(-1, F), axis=1))
 
 
+@pytest.mark.parametrize("name", ["g2_scan_64_r050.npz", "g5b_scan_1200_raw.npz"])
+def test_scan_state_resident_on_device_golden(name):
+    """kspec_scan_state_init / kspec_scan_pass / kspec_scan_state_fetch: the same passes with Fft.Cur/Max/Min/Avg kept in HBM
+    between passes, against the reference's golden vectors (one fetch per pass here, to compare every pass)"""
+    g = load_golden(name)
+    p = g["params"]
+    if "step_bufs" not in g:
+        g0 = load_golden("g5b_scan_1200_cur.npz")
+        g["step_bufs"], g["window"] = g0["step_bufs"], g0["window"]
+    F, S = p["fftSize"], p["fullSize"]
+    samples = np.ascontiguousarray(g["step_bufs"]).reshape(-1)
+    geo = O.scan_geometry(p["startFreq"], p["endFreq"], p["samplingRate"], F, p["scanRangeNonOverlap"])
+    _, total, steps = geo
+    with Plan(F, S, p["curScanNonOverlap"], g["window"], p["curScanCumuMode"], _ffi.in_format(samples), precision="auto") as plan:
+        plan.scan_state_init(O.scan_init_state(total, p["gain"], p["minAmp4Clip"]))
+        for ps in range(p["nPass"]):
+            ok = np.array([0 if (ps == 0 and s in p["failSteps"]) else 1 for s in range(p["nSteps"])], dtype=np.uint8)
+            plan.scan_pass(samples, p["nSteps"], [s["i_start"] for s in steps], [s["i_done"] for s in steps], p["minAmp4Clip"], p["gain"], ps,
+                           step_ok=ok, base_is_raw=p["bScanRangeBaseDataIsRaw"])
+            st = plan.scan_state_fetch()
+            for k in ("cur", "max", "min", "avg"):
+                assert np.max(np.abs(st[k] - g["p%d_%s" % (ps, k)])) < F64_TOL, (ps, k)
+
+
+@pytest.mark.parametrize("fmt,prec", [("c64", "f64"), ("u8", "f32")])
+def test_scan_pass_chunked_ingest_equals_scan_batch(fmt, prec):
+    """a pass large enough for the chunked, overlapped host->device path (330 steps x 32768 samples): device-resident state
+    over three passes, fetched once at the end, against kspec_scan_batch pass by pass and against the oracle"""
+    F, r, R, gain, n_groups = 4096, 0.5, 0.5, 19.1, 165
+    S = O.full_size(F, FS)
+    geo = O.scan_geometry(100e6, 100e6 + n_groups * FS, FS, F, R)
+    _, total, steps = geo
+    ns = len(steps)
+    x = np.concatenate([synth.step_tones(s % 40, S, dtype=np.complex128) for s in range(ns)])
+    raw = synth.to_u8_iq(x) if fmt == "u8" else x.astype(np.complex64)
+    assert raw.nbytes > (64 << 20) or fmt == "u8"
+    win = O.window_table("hanning", F)
+    i_start, i_done = [s["i_start"] for s in steps], [s["i_done"] for s in steps]
+    ok = np.ones(ns, dtype=np.uint8)
+    ok[7] = 0
+    with Plan(F, S, r, win, "AVG", _ffi.in_format(raw), precision=prec) as plan:
+        st = O.scan_init_state(total, gain)
+        plan.scan_state_init(st)
+        for ps in range(3):
+            plan.scan_pass(raw, ns, i_start, i_done, O.MIN_AMP4CLIP, gain, ps, step_ok=ok if ps == 1 else None)
+            plan.scan_batch(raw, ns, i_start, i_done, total, O.MIN_AMP4CLIP, gain, st, ps, step_ok=ok if ps == 1 else None)
+        res = plan.scan_state_fetch()
+        d = plan.dev_alloc(raw.nbytes)
+        plan.dev_upload(d, raw)
+        plan.scan_pass(d, ns, i_start, i_done, O.MIN_AMP4CLIP, gain, 3, on_device=True)
+        plan.scan_batch(raw, ns, i_start, i_done, total, O.MIN_AMP4CLIP, gain, st, 3)
+        res_dev = plan.scan_state_fetch(which=("cur", "avg"))
+        plan.dev_free(d)
+    tol = 1e-4 if prec == "f32" else 1e-9
+    assert np.max(np.abs(res_dev["cur"] - st["cur"])) < tol and np.max(np.abs(res_dev["avg"] - st["avg"])) < tol
+    if prec == "f64":
+        xin = raw.astype(np.complex128)
+        lin = [O.curscan(xin[k * S:(k + 1) * S], F, r, win) for k in range(ns)]
+        ref = O.scan_init_state(total, gain)
+        for ps in range(3):
+            ref = O.scan_pass(lin, [bool(v) for v in (ok if ps == 1 else np.ones(ns))], geo, gain, ref, ps)
+        for k in ("cur", "max", "min", "avg"):
+            assert np.max(np.abs(res[k] - ref[k])) < F64_TOL, k
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # seeded oracle-vs-CUDA sweeps (sizes the oracle finishes in seconds)
 # ---------------------------------------------------------------------------------------------------------------
