@@ -150,8 +150,15 @@ __device__ __forceinline__ void r32_stage0(float2 (&b)[32], const float (&win)[3
 // raw sample -> float2 without scale or window (both live in the window registers of the R32 kernels)
 template <int INFMT> struct R32Raw;
 template <> struct R32Raw<KSPEC_IN_U8_IQ> {
-    typedef uchar2 raw_t;
-    static __device__ __forceinline__ float2 get(uchar2 v, float off) { return make_float2((float)v.x - off, (float)v.y - off); }
+    typedef unsigned short raw_t;                 // I in the low byte, Q in the high byte (octave/load_rtlsdr.m:8-12)
+    // byte -> float without the conversion unit (I2F runs at a quarter of the FP32 rate): 0x4B000000 | b is the float
+    // 2^23 + b exactly, one byte-permute per component, then two packed subtractions; same value as (float)b - off
+    static __device__ __forceinline__ float2 get(unsigned short v, float off) {
+        const float2 m = make_float2(__uint_as_float(__byte_perm((unsigned)v, 0x4B000000u, 0x7540)),
+                                     __uint_as_float(__byte_perm((unsigned)v, 0x4B000000u, 0x7541)));
+        const float2 b = __fadd2_rn(m, make_float2(-8388608.0f, -8388608.0f));
+        return __fadd2_rn(b, make_float2(-off, -off));
+    }
 };
 template <> struct R32Raw<KSPEC_IN_C64> {
     typedef float2 raw_t;
