@@ -288,7 +288,8 @@ __device__ __forceinline__ void r32_build_twiddles(float2* stw, const float2* __
     }
 }
 
-template <int INFMT>
+// DYN: scans beyond a team's first are tickets from a global counter instead of the static stride (see below)
+template <int INFMT, bool DYN>
 __global__ void __launch_bounds__(R32Cfg::CTA, 1) curscan_r32_kernel(const ScanParams p) {
     using C = R32Cfg;
     using SC = R32Stage<INFMT>;
@@ -297,6 +298,7 @@ __global__ void __launch_bounds__(R32Cfg::CTA, 1) curscan_r32_kernel(const ScanP
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t mbar_all[TEAMS];
+    __shared__ int32_t nextScanAll[TEAMS];                         // next scan of each team (dynamic scheduling, see below)
     __shared__ int32_t foffs[C::MAX_FRAMES];                       // K:386 frame starts inside a scan
     const int team = threadIdx.x / NT;
     const int tid = threadIdx.x % NT;                              // = rho in stage 1: owns bins tid + 64 kappa
@@ -332,11 +334,15 @@ __global__ void __launch_bounds__(R32Cfg::CTA, 1) curscan_r32_kernel(const ScanP
     const bool avgScaled = p.cumuMode == KSPEC_CUMU_AVG && p.nFrames <= 96;       // see curscan_smem.cuh
     const float linScale = avgScaled ? (float)ldexp(p.linScale, -(p.nFrames - 1)) : (float)p.linScale;
     const int slot = blockIdx.x * TEAMS + team;
-    const int64_t scansPerIter = (int64_t)gridDim.x * TEAMS;
-    const int64_t iters = (p.nScans + scansPerIter - 1) / scansPerIter;
-    const int64_t totalFrames = iters * p.nFrames;
-    const uint64_t polStream = l2_policy_evict_first();            // samples stream through L2 once (plus the overlap re-read)
-    const uint64_t polKeep = l2_policy_evict_last();               // the per-team Max/Min partials stay L2 resident
+    // Team `slot` starts with scan `slot`.  Static form: it goes on with slot + nSlots, ...  Dynamic form (DYN): every further
+    // scan is a ticket from a global counter (one atomic per scan, fetched a whole scan ahead), because a static partition makes
+    // the launch as long as its slowest team -- a team whose SM was still busy with another kernel (the NCCL exchange of the
+    // previous batch of a sharded capture) when the grid started, or the last wave of a batch that is far from a multiple of
+    // the team count.  The launcher picks the form (the ticket costs ~2 % on a full, undisturbed launch).
+    const int nSlots = (int)gridDim.x * TEAMS;
+    const int nScans32 = (int)p.nScans;                           // the launcher keeps batches below 2^31 scans
+    // L2 policies are created where they are used (one instruction; two registers each if they were kept): the samples stream
+    // through L2 once (evict first), the per-team Max/Min partials stay L2 resident (evict last)
 
     // leader only: fetch frame f of scan sc into the stage buffer.  General mode: one bulk copy of the 16-byte granules around
     // the frame (offsets can be odd), clipped at the end of the batch (see curscan_smem.cuh).  Ring mode (every frame starts
@@ -346,6 +352,7 @@ __global__ void __launch_bounds__(R32Cfg::CTA, 1) curscan_r32_kernel(const ScanP
     const bool ring = p.hopRing != 0;
     constexpr int HALF_BYTES = (F / 2) * SC::EB;
     auto issue = [&](int64_t sc, int f) {
+        const uint64_t polStream = l2_policy_evict_first();
         if (ring) {
             const int h = f == 0 ? 0 : f + 1;                      // first hop to fetch
             const uint32_t bytes = f == 0 ? 2 * HALF_BYTES : HALF_BYTES;
@@ -369,21 +376,32 @@ __global__ void __launch_bounds__(R32Cfg::CTA, 1) curscan_r32_kernel(const ScanP
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (leader && totalFrames > 0) issue(slot < p.nScans ? slot : p.nScans - 1, 0);
+    if (slot >= p.nScans) {
+        // a team without work still owns a Max/Min partial: the identities of max / min over amplitudes
+        if (p.wantStats) {
+            float* wmax = reinterpret_cast<float*>(p.wsMax) + (int64_t)slot * F;
+            float* wmin = reinterpret_cast<float*>(p.wsMin) + (int64_t)slot * F;
+            for (int i = tid; i < F; i += NT) { wmax[i] = 0.0f; wmin[i] = pos_inf<float>(); }
+        }
+        return;
+    }
+    if (leader) issue(slot, 0);
 
-    int64_t g = 0;
-    for (int64_t it = 0; it < iters; ++it) {
-        const int64_t scan = it * scansPerIter + slot;
-        const bool valid = scan < p.nScans;
-        const int64_t scanC = valid ? scan : p.nScans - 1;
-        const int64_t sbase = scanC * p.scanStride;
+    uint32_t g = 0;                                                // frames this team has processed (mbarrier parity)
+    bool firstScan = true;
+    int nxtLeader = 0;
+    for (int scan = slot; scan < nScans32; scan = DYN ? nextScanAll[team] : scan + nSlots) {
+        const bool valid = true;
+        const int64_t it = firstScan ? 0 : 1;
+        firstScan = false;
+        const int64_t sbase = (int64_t)scan * p.scanStride;
 
         float acc[P];
         float avgW = 1.0f;
         for (int f = 0; f < p.nFrames; ++f, ++g) {
             float2 b[P];
             {
-                mbar_wait(mbar, (uint32_t)(g & 1));
+                mbar_wait(mbar, g & 1);
                 const int mis = (SC::SLACK > 0 && !ring) ? (((int)sbase + foffs[f]) & (SC::SLACK - 1)) : 0;
                 const typename IN::raw_t* sp0 = reinterpret_cast<const typename IN::raw_t*>(stage + ((ring && (f & 1)) ? HALF_BYTES : 0)) + mis + j;
                 const typename IN::raw_t* sp1 = reinterpret_cast<const typename IN::raw_t*>(stage + ((ring && (f & 1)) ? 0 : HALF_BYTES)) + mis + j;
@@ -394,11 +412,18 @@ __global__ void __launch_bounds__(R32Cfg::CTA, 1) curscan_r32_kernel(const ScanP
             }
             // every thread of the team is past its stage reads and (program order) past the previous frame's exchange reads
             sync();
-            if (leader && g + 1 < totalFrames) {
-                const bool lastF = f + 1 == p.nFrames;
-                int64_t sc = lastF ? scan + scansPerIter : scanC;
-                if (sc >= p.nScans) sc = p.nScans - 1;
-                issue(sc, lastF ? 0 : f + 1);
+            if (leader) {
+                if constexpr (DYN) {
+                    if (f == 0) nxtLeader = (int)atomicAdd(p.scanCounter, 1u) + nSlots;      // needed a whole scan from now
+                } else {
+                    nxtLeader = scan + nSlots;
+                }
+                if (f + 1 < p.nFrames) {
+                    issue(scan, f + 1);
+                } else {
+                    if constexpr (DYN) nextScanAll[team] = nxtLeader;                     // read by the team after the epilogue's barriers
+                    if (nxtLeader < nScans32) issue(nxtLeader, 0);
+                }
             }
             r32_stage0(b, win, reinterpret_cast<const float4*>(stw) + tid, omega, ex + (16 * upper) * PITCH + jp);
             sync();
@@ -445,7 +470,7 @@ __global__ void __launch_bounds__(R32Cfg::CTA, 1) curscan_r32_kernel(const ScanP
 #pragma unroll
         for (int m = 0; m < P; ++m) erow[(tid + NT * m) ^ (F >> 1)] = acc[m] * linScale;
         sync();
-        const bool hmDone = scan_epilogue_rows<NT>(p, erow, scan, valid, it, slot, tid, polKeep);
+        const bool hmDone = scan_epilogue_rows<NT>(p, erow, scan, valid, it, slot, tid, l2_policy_evict_last());
         if (p.hm != nullptr && !hmDone) {
             sync();
             // _data_plotcompress (K:184-200): W groups of adjacent bins
@@ -468,13 +493,13 @@ __global__ void __launch_bounds__(R32Cfg::CTA, 1) curscan_r32_kernel(const ScanP
     }
 }
 
-template <int INFMT>
+template <int INFMT, bool DYN = false>
 static int launch_r32(const ScanParams& p, int grid, cudaStream_t st, SmemKernelInfo* info) {
     using SC = R32Stage<INFMT>;
     if constexpr (!SC::OK) {
         return (int)cudaErrorInvalidValue;
     } else {
-        auto k = curscan_r32_kernel<INFMT>;
+        auto k = curscan_r32_kernel<INFMT, DYN>;
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SC::SMEM_BYTES);
         if (e != cudaSuccess) return (int)e;
         if (info) {

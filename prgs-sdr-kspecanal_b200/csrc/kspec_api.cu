@@ -73,6 +73,7 @@ struct kspec_plan {
     bool frameParallelOff = false; // KSPEC_FRAME_PARALLEL=0 at plan creation
     size_t chunkBytes = (size_t)256 << 20;   // pipelined host batches; KSPEC_PIPELINE_CHUNK_BYTES at plan creation
     int64_t statsSeq = 0;          // bumped by every batch that rewrites `stats` (kspec_comm_join checks it)
+    bool shardedHint = false;      // the current batch is a shard of a larger capture (scanIndexBase / nScansTotal)
     bool r32Off = false;          // KSPEC_NO_R32=1 at plan creation: keep the 16/16/8 layouts (A/B runs, tests)
     bool r32Pipe = false;         // KSPEC_R32_PIPE=1 at plan creation: the two-role pipeline (curscan_r32p.cuh) instead of the one-role kernel; kiR32 describes it
     int64_t convSize = 0;
@@ -89,7 +90,7 @@ struct kspec_plan {
     void* dTw = nullptr;
     void* dTwLin = nullptr;
     // grow-only workspaces
-    DevBuf in, rows, hm, wsMax, wsMin, avgRows, adj, adj64, carry, stats, wide, acc, l2, misc, frameRows, vbase, scanState, scanGeo;
+    DevBuf in, rows, hm, wsMax, wsMin, avgRows, adj, adj64, carry, stats, wide, acc, l2, misc, frameRows, vbase, scanState, scanGeo, sched;
     int64_t scanTotal = 0;                         // entries of the device-resident stepped-scan state (0: none)
     int64_t vbaseScans = 0;                        // scans covered by the frame-parallel base table in vbase
     // what the last *_dev batch left behind (for fetch)
@@ -223,6 +224,17 @@ int run_engine(kspec_plan* pl, ScanParams& p, int* slotsOut, int* statsLinear = 
             bool ring = ((size_t)pl->S * in_elem_bytes(pl->inFmt)) % 16 == 0 && ((uintptr_t)p.samples % 16) == 0 && !pl->r32Pipe;
             for (size_t f = 0; ring && f < pl->offs.size(); ++f) ring = pl->offs[f] == (int64_t)f * (pl->F / 2);
             p.hopRing = ring ? 1 : 0;
+            // dynamic scan tickets when a static partition would leave a long tail: a shard of a multi-GPU capture (the previous
+            // batch's NCCL exchange may still hold SMs when this grid starts) or a last wave that is mostly empty
+            const double waves = (double)p.nScans / (double)slots;
+            const bool ragged = ceil(waves) / waves > 1.05;
+            p.scanCounter = nullptr;
+            if (pl->shardedHint || ragged) {
+                int rc2;
+                if ((rc2 = pl->sched.reserve(64))) return rc2;
+                CK(cudaMemsetAsync(pl->sched.p, 0, 4, pl->st));       // the scan ticket counter of this launch
+                p.scanCounter = (unsigned int*)pl->sched.p;
+            }
         }
         int e;
         if (r32 && pl->r32Pipe) e = pl->inFmt == KSPEC_IN_U8_IQ ? launch_r32p_u8(p, grid, pl->st, nullptr) : launch_r32p_c64(p, grid, pl->st, nullptr);
@@ -485,7 +497,7 @@ int kspec_plan_destroy(kspec_plan* pl) {
     if (pl->big) bigfft_destroy(pl->big);
     if (pl->mixed) mixedradix_destroy(pl->mixed);
     for (DevBuf* b : {&pl->in, &pl->rows, &pl->hm, &pl->wsMax, &pl->wsMin, &pl->avgRows, &pl->adj, &pl->adj64, &pl->carry, &pl->stats,
-                      &pl->wide, &pl->acc, &pl->l2, &pl->misc, &pl->frameRows, &pl->vbase, &pl->scanState, &pl->scanGeo}) b->release();
+                      &pl->wide, &pl->acc, &pl->l2, &pl->misc, &pl->frameRows, &pl->vbase, &pl->scanState, &pl->scanGeo, &pl->sched}) b->release();
     if (pl->dOffs) cudaFree(pl->dOffs);
     if (pl->dWin) cudaFree(pl->dWin);
     if (pl->dTw) cudaFree(pl->dTw);
@@ -603,6 +615,7 @@ int kspec_zerospan_batch_dev(kspec_plan* pl, const void* dSamples, int64_t nScan
     int W = 0, rc;
     if ((rc = zerospan_check(pl, dSamples, nScans, hmMode, xRes, rowsKind, wantHm, mx, mn, av, carry, scanIndexBase, nScansTotal, &W))) return rc;
     DeviceGuard guard(pl->device);
+    pl->shardedHint = nScansTotal != nScans;
     if ((rc = zerospan_prepare(pl, nScans, W, rowsKind, wantHm != 0, adj, mx, mn, av, carry))) return rc;
     if ((rc = zerospan_part(pl, dSamples, nScans, 0, gain, adj != nullptr, hmMode, W, rowsKind, wantHm != 0,
                             carry ? (const double*)pl->carry.p : nullptr, (!carry && scanIndexBase == 0) ? 1 : 0,

@@ -42,6 +42,7 @@ struct ScanParams {
     // linear-row engines only: accumulation rows stored [k1][k2] with bin k = k1 + 2^accL1 * k2 (0: natural order)
     int32_t accL1, accL2;
     int32_t accShifted;        // acc rows are already fftshift-ed and normalised (zeroSpanPlay records)
+    unsigned int* scanCounter; // R32 kernel: device counter (zeroed before the launch) that hands out scans beyond the first per team
     int32_t hopRing;           // R32 kernels: every frame starts fftSize/2 after the previous one and scans are 16-byte aligned
 };
 

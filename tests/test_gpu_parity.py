@@ -395,6 +395,24 @@ def test_r32_layout_ragged(fmt, cumu, r, wname):
     assert np.max(np.abs(lin["hm_rows"] - ref2["hm_rows"])) < DB_TOL
 
 
+def test_r32_static_and_ticket_schedules_agree():
+    """the 32 x 2 x 32 kernel hands out scans by a static stride (full, undisturbed launches) or by tickets from a global
+    counter (ragged batches, shards of a multi-GPU capture): the same scans must give bit-identical rows either way"""
+    F, r, gain, xres = 2048, 0.5, 19.1, 512
+    S = O.full_size(F, FS)
+    full, ragged = 6 * 148 * 2, 6 * 148 * 2 + 300
+    x = synth.tones_noise(ragged * S, seed=33)
+    win = O.window_table("hanning", F)
+    with Plan(F, S, r, win, "AVG", _ffi.IN_C64, precision="f32") as plan:
+        a = plan.zerospan_batch(x[:full * S], full, gain, xres, "MAX", rows="db")                    # 2.0 waves: static stride
+        b = plan.zerospan_batch(x, ragged, gain, xres, "MAX", rows="db")                             # 2.17 waves: tickets
+        c = plan.zerospan_batch(x[:full * S], full, gain, xres, "MAX", rows="db", scan_index_base=0, n_scans_total=4 * full)   # shard: tickets
+    assert np.array_equal(a["rows"], b["rows"][:full]) and np.array_equal(a["hm_rows"], b["hm_rows"][:full])
+    assert np.array_equal(a["rows"], c["rows"]) and np.array_equal(a["max"], c["max"]) and np.array_equal(a["min"], c["min"])
+    ref = O.log_nogain(O.curscan(x[(ragged - 1) * S:ragged * S].astype(np.complex128), F, r, win), gain)
+    assert np.max(np.abs(b["rows"][-1] - ref)) < DB_TOL
+
+
 def test_cfg2_full_size_quickfullscan():
     """BASELINE cfg 2 at full size: quickFullScan 30 MHz..1.5 GHz -> 613 groups, 39 232 entries, fftSize 64, ones, r = 0.1
     (71 frames per step); 613 steps at scanRangeNonOverlap 1.0 and 1226 at the alias' default 0.5; two passes; vs the oracle."""
