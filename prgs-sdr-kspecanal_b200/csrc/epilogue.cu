@@ -16,18 +16,23 @@ namespace {
 
 __device__ __forceinline__ double d_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
 
-// block = (32 bins) x (FIN_Y slot groups): the per-team partials are reduced by FIN_Y threads per bin in parallel
-// (a batch of the headline shape leaves 592 partials), then the y == 0 thread finishes the bin.
-constexpr int FIN_Y = 16;
+// block = (FIN_X bins) x (FIN_Y slot groups): the per-team partials (888 of them after a batch of the headline shape) are reduced
+// by FIN_Y threads per bin in parallel over many small CTAs (the kernel is pure latency: 14 MB out of L2), then a tree in shared
+// memory and the y == 0 thread finishes the bin.
+constexpr int FIN_X = 8, FIN_Y = 64;
 template <typename T>
-__global__ void stats_finish_kernel(const T* __restrict__ wsMax, const T* __restrict__ wsMin, int slots,
+__global__ void __launch_bounds__(FIN_X * FIN_Y) stats_finish_kernel(const T* __restrict__ wsMax, const T* __restrict__ wsMin, int slots,
                                     const T* __restrict__ avgRows, int avgWin, int F, const double* __restrict__ carry,
                                     int firstIsSeed, double avgScale, double* __restrict__ out, int partialsLinear, T gain) {
-    __shared__ double shMax[FIN_Y][33], shMin[FIN_Y][33];
-    const int j = blockIdx.x * 32 + threadIdx.x;
+    __shared__ double shMax[FIN_Y][FIN_X + 1], shMin[FIN_Y][FIN_X + 1], shAvg[FIN_Y][FIN_X + 1];
+    const int j = blockIdx.x * FIN_X + threadIdx.x;
     const bool inb = j < F;
     double mx = -d_inf(), mn = d_inf();
+    // the rows of the Avg recurrence (at most AVG_WINDOW = FIN_Y of them) are fetched by the y threads side by side: the
+    // sequential recurrence below then reads shared memory instead of paying one L2 round trip per row
+    for (int r = threadIdx.y; r < avgWin && inb; r += FIN_Y) shAvg[r][threadIdx.x] = (double)avgRows[(int64_t)r * F + j];
     if (inb) {
+#pragma unroll 4
         for (int s = threadIdx.y; s < slots; s += FIN_Y) {
             mx = fmax(mx, (double)wsMax[(int64_t)s * F + j]);
             mn = fmin(mn, (double)wsMin[(int64_t)s * F + j]);
@@ -36,11 +41,16 @@ __global__ void stats_finish_kernel(const T* __restrict__ wsMax, const T* __rest
     shMax[threadIdx.y][threadIdx.x] = mx;
     shMin[threadIdx.y][threadIdx.x] = mn;
     __syncthreads();
-    if (threadIdx.y != 0 || !inb) return;
-    for (int y = 1; y < FIN_Y; ++y) {
-        mx = fmax(mx, shMax[y][threadIdx.x]);
-        mn = fmin(mn, shMin[y][threadIdx.x]);
+    for (int h = FIN_Y / 2; h > 0; h >>= 1) {
+        if (threadIdx.y < h) {
+            shMax[threadIdx.y][threadIdx.x] = fmax(shMax[threadIdx.y][threadIdx.x], shMax[threadIdx.y + h][threadIdx.x]);
+            shMin[threadIdx.y][threadIdx.x] = fmin(shMin[threadIdx.y][threadIdx.x], shMin[threadIdx.y + h][threadIdx.x]);
+        }
+        __syncthreads();
     }
+    if (threadIdx.y != 0 || !inb) return;
+    mx = shMax[0][threadIdx.x];
+    mn = shMin[0][threadIdx.x];
     if (partialsLinear) {
         // the R32 kernels reduce the normalised LINEAR amplitudes (the dB map is monotone): the same conversion as the rows get
         mx = (double)(to_db((T)mx) - gain);
@@ -53,9 +63,13 @@ __global__ void stats_finish_kernel(const T* __restrict__ wsMax, const T* __rest
     double a;
     int r = 0;
     if (carry) a = carry[2 * F + j];
-    else if (firstIsSeed) { a = (double)avgRows[j]; r = 1; }
+    else if (firstIsSeed) { a = (avgWin <= FIN_Y) ? shAvg[0][threadIdx.x] : (double)avgRows[j]; r = 1; }
     else a = 0.0;
-    for (; r < avgWin; ++r) a = (a + (double)avgRows[(int64_t)r * F + j]) / 2;
+    if (avgWin <= FIN_Y) {
+        for (; r < avgWin; ++r) a = (a + shAvg[r][threadIdx.x]) / 2;
+    } else {
+        for (; r < avgWin; ++r) a = (a + (double)avgRows[(int64_t)r * F + j]) / 2;
+    }
     out[j] = mx;
     out[F + j] = mn;
     out[2 * F + j] = (avgScale == 0.0) ? 0.0 : a * avgScale;
@@ -328,11 +342,11 @@ void launch_stats_finish(int prec, const void* wsMax, const void* wsMin, int slo
                          const double* carry, int firstIsSeed, double avgScale, double* out, cudaStream_t st, int partialsLinear,
                          double gain) {
     if (prec == KSPEC_PREC_F32)
-        stats_finish_kernel<float><<<nblk(F, 32), dim3(32, FIN_Y), 0, st>>>((const float*)wsMax, (const float*)wsMin, slots,
+        stats_finish_kernel<float><<<nblk(F, FIN_X), dim3(FIN_X, FIN_Y), 0, st>>>((const float*)wsMax, (const float*)wsMin, slots,
                                                                  (const float*)avgRows, avgWin, F, carry, firstIsSeed, avgScale, out,
                                                                  partialsLinear, (float)gain);
     else
-        stats_finish_kernel<double><<<nblk(F, 32), dim3(32, FIN_Y), 0, st>>>((const double*)wsMax, (const double*)wsMin, slots,
+        stats_finish_kernel<double><<<nblk(F, FIN_X), dim3(FIN_X, FIN_Y), 0, st>>>((const double*)wsMax, (const double*)wsMin, slots,
                                                                   (const double*)avgRows, avgWin, F, carry, firstIsSeed, avgScale, out,
                                                                   partialsLinear, gain);
 }
