@@ -486,7 +486,7 @@ def run_ours(args):
     return 0
 
 
-def parity_check(world, rank, local, comm):
+def parity_check(world, rank, local, comm, peer=False):
     """N > 1, outside every timed region: BASELINE cfg-3 shape (fftSize 8192, kaiser(64), 75 % overlap, float64), 96 scans
     per rank sharded by scan range.  Every rank runs its shard (host path + NCCL on host vectors, then device-resident path
     + asynchronous NCCL on the plan's vectors); rank 0 also runs ONE plan over the whole capture.  K:460-476."""
@@ -512,13 +512,23 @@ def parity_check(world, rank, local, comm):
         comm.join(plan)
         dev = plan.zerospan_fetch(rows=False, hm=False)
         mark("parity: device all-reduce done")
+        pex = None
+        if peer:
+            comm.peer_setup(plan)                # same fftSize as the timed plan: the exchange moves to this plan
+            plan.zerospan_batch_dev(d, per, GAIN, XRES, "MAX", scan_index_base=a, n_scans_total=n)
+            pex = plan.zerospan_fetch(rows=False, hm=False)
+            if comm.peer_timed_out():
+                pex = None
+            mark("parity: peer exchange done")
         plan.dev_free(d)
         if rank != 0:
             return None
         one = plan.zerospan_batch(x, n, GAIN, XRES, "MAX")
     err = {}
     ok = True
-    for name, got in (("host_allreduce", out), ("device_allreduce", dev)):
+    if peer and pex is None:
+        ok = False
+    for name, got in (("host_allreduce", out), ("device_allreduce", dev)) + ((("peer_exchange", pex),) if pex is not None else ()):
         e = {k: float(np.max(np.abs(got[k] - one[k]))) for k in ("max", "min", "avg")}
         ok = ok and np.array_equal(got["max"], one["max"]) and np.array_equal(got["min"], one["min"]) and e["avg"] <= 1e-9
         err[name] = e
@@ -591,6 +601,10 @@ def run_cfg3(args):
     pinned_out = _ffi.PinnedBuffer(n * XRES * 8)
     host_out = {"hm_rows": pinned_out.view(np.float64).reshape(n, XRES)}
     comm = _make_comm(world, rank, local, dist) if world > 1 else None
+    # KSPEC_PEER_EXCHANGE=1: the exchange is the tail of the statistics kernel (peer-memory writes over NVLink) instead of NCCL
+    peer = comm is not None and os.environ.get("KSPEC_PEER_EXCHANGE", "1") == "1"
+    if peer:
+        comm.peer_setup(plan)
 
     def barrier():
         plan.sync()
@@ -598,6 +612,11 @@ def run_cfg3(args):
             dist.barrier()
 
     def step_dev(exchange=True):
+        if peer:
+            # sharded (n_scans_total) -> the batch ends with the peer exchange; "without exchange" = the same shard as a capture of its own
+            plan.zerospan_batch_dev(d, n, GAIN, XRES, "MAX", rows=None, want_hm=True, scan_index_base=a if exchange else 0,
+                                    n_scans_total=n_total if exchange else n)
+            return
         plan.zerospan_batch_dev(d, n, GAIN, XRES, "MAX", rows=None, want_hm=True, scan_index_base=a, n_scans_total=n_total)
         if comm is not None and exchange:
             comm.allreduce_plan_stats(plan)
@@ -629,12 +648,13 @@ def run_cfg3(args):
         step_e2e()
     plan.sync()
     e2e_s = _max_over_ranks((time.perf_counter() - t0) / args.steps, dist, local)
-    parity = parity_check(world, rank, local, comm) if comm is not None else None
+    parity = parity_check(world, rank, local, comm, peer=peer) if comm is not None else None
     if rank == 0:
         total = n_total * S3
         line = {"metric": "IQ Msamples/s via window+FFT+max/min/avg, BASELINE cfg 3 (fftSize 8192 kaiser 75 % overlap, 60 s capture)",
                 "value": total / (ms_dev * 1e-3) / 1e6, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_dev, "ms_per_step_without_exchange": ms_noex, "exchange_share": max(0.0, 1.0 - ms_noex / ms_dev),
+                "exchange": "peer-memory writes from stats_finish_kernel + peer_combine_kernel (kspec_comm_peer_setup)" if peer else ("NCCL all-reduce (MAX, MIN, SUM)" if comm is not None else "none"),
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "zeroSpan fftSize 8192 kaiser(64) 75 %% overlap cumuAVG float64, %d scans x %d samples (60 s at 2.4 MS/s) "
                                        "sharded by scan range over %d GPU(s), complex64 ingest" % (n_total, S3, world), "scans_rank0": n},

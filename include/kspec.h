@@ -232,6 +232,16 @@ int kspec_comm_allreduce_plan(kspec_comm* comm, kspec_plan* plan);
  * one of the two has consumed it or another all-reduce has reused the communicator's buffer. */
 int kspec_comm_join(kspec_comm* comm, kspec_plan* plan);
 int kspec_comm_fetch_reduced(kspec_comm* comm, double* max, double* min, double* avg, int64_t n);
+/* The exchange as the TAIL OF THE COMPUTE KERNEL instead of a collective call: kspec_comm_peer_setup (collective: every rank calls
+ * it once, with its plan) gives every rank a symmetric device buffer, maps the peers' buffers through CUDA IPC (NVLink peer access)
+ * and attaches the exchange to the plan.  From then on every kspec_zerospan_batch_dev call of that plan that is a shard of a larger
+ * capture (nScansTotal != nScans, carry == 0) ends with its statistics kernel writing this rank's Max / Min / pre-weighted Avg
+ * straight into every rank's buffer and raising a flag there, and a small second kernel waits for the flags of all ranks and
+ * reduces: kspec_zerospan_fetch returns Fft.Max / Min / Avg of the WHOLE capture, no kspec_comm_allreduce_* call needed (and none may
+ * be mixed in for that plan).  Every rank must run the same sequence of such batches.  A rank that never arrives trips a ~2 s
+ * time-out in the waiting kernel: kspec_comm_peer_status reports it (the statistics are then not reduced).  Up to 8 ranks. */
+int kspec_comm_peer_setup(kspec_comm* comm, kspec_plan* plan);
+int kspec_comm_peer_status(kspec_comm* comm, int* timedOut);
 int kspec_comm_finalize(kspec_comm* comm);
 
 #ifdef __cplusplus

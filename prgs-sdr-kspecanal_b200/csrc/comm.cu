@@ -8,6 +8,7 @@
 #include <nccl.h>
 #include <string.h>
 #include <new>
+#include <vector>
 
 namespace kspec {
 
@@ -18,6 +19,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
@@ -37,11 +39,12 @@ NcclApi& api() {
     a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.h, "ncclGetUniqueId");
     a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.h, "ncclCommInitRank");
     a.AllReduce = (decltype(a.AllReduce))dlsym(a.h, "ncclAllReduce");
+    a.AllGather = (decltype(a.AllGather))dlsym(a.h, "ncclAllGather");
     a.GroupStart = (decltype(a.GroupStart))dlsym(a.h, "ncclGroupStart");
     a.GroupEnd = (decltype(a.GroupEnd))dlsym(a.h, "ncclGroupEnd");
     a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.h, "ncclCommDestroy");
     a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.h, "ncclGetErrorString");
-    a.ok = a.GetUniqueId && a.CommInitRank && a.AllReduce && a.GroupStart && a.GroupEnd && a.CommDestroy && a.GetErrorString;
+    a.ok = a.GetUniqueId && a.CommInitRank && a.AllReduce && a.AllGather && a.GroupStart && a.GroupEnd && a.CommDestroy && a.GetErrorString;
     return a;
 }
 
@@ -69,6 +72,10 @@ struct kspec_comm {
     size_t cap = 0;
     int64_t pendingN = 0;      // length of the vectors of the last asynchronous plan reduction held in buf (0: none)
     int64_t pendingSeq = -1;   // kspec_plan batch sequence number that reduction snapshotted
+    // peer-memory exchange (kspec_comm_peer_setup): this rank's symmetric buffer and the peers' buffers mapped through CUDA IPC
+    PeerExchange px;
+    void* sym = nullptr;
+    void* peerMapped[KSPEC_MAX_PEERS] = {};
 };
 
 namespace {
@@ -250,9 +257,101 @@ int kspec_comm_fetch_reduced(kspec_comm* c, double* mx, double* mn, double* av, 
     return KSPEC_OK;
 }
 
+// ---- the exchange as the tail of the compute kernel: peer-memory writes instead of a collective call -------------------------
+int kspec_comm_peer_setup(kspec_comm* c, kspec_plan* plan) {
+    if (!c || !plan) { set_error("bad peer setup arguments"); return KSPEC_ERR_ARG; }
+    if (c->nRanks > KSPEC_MAX_PEERS) { set_error("peer exchange supports up to %d ranks", KSPEC_MAX_PEERS); return KSPEC_ERR_UNSUPPORTED; }
+    DevGuard guard(c->device);
+    if (c->sym) {
+        // already set up: attach another plan of the same fftSize as well (every rank must do the same; the plans share the
+        // buffers and the sequence, so their sharded batches must be issued in the same order on every rank)
+        return plan_attach_peer(plan, &c->px);
+    }
+    double* stats = nullptr;
+    int F = 0;
+    cudaStream_t pst = nullptr;
+    {   // fftSize of the plan (plan_stats_view needs a batch; kspec_plan_info does not)
+        kspec_plan_info_t info;
+        if (kspec_plan_info(plan, &info) != KSPEC_OK) return KSPEC_ERR_ARG;
+        F = info.fft_size;
+        (void)stats; (void)pst;
+    }
+    const int n = c->nRanks;
+    const size_t dataBytes = (size_t)2 * n * 3 * F * 8, flagBytes = (size_t)2 * n * 8;
+    const size_t total = dataBytes + flagBytes + 256;
+    CCK(cudaMalloc(&c->sym, total));
+    CCK(cudaMemset(c->sym, 0, total));
+    cudaIpcMemHandle_t mine;
+    CCK(cudaIpcGetMemHandle(&mine, c->sym));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    // all-gather of the 64-byte handles over the communicator that already exists
+    char* dH = nullptr;
+    CCK(cudaMalloc(&dH, (size_t)n * 64));
+    CCK(cudaMemcpyAsync(dH + (size_t)c->rank * 64, &mine, 64, cudaMemcpyHostToDevice, c->st));
+    NCK(api().AllGather(dH + (size_t)c->rank * 64, dH, 64, ncclChar, c->comm, c->st));
+    std::vector<cudaIpcMemHandle_t> all(n);
+    CCK(cudaMemcpyAsync(all.data(), dH, (size_t)n * 64, cudaMemcpyDeviceToHost, c->st));
+    CCK(cudaStreamSynchronize(c->st));
+    cudaFree(dH);
+    c->px = PeerExchange();
+    c->px.nRanks = n; c->px.rank = c->rank; c->px.F = F;
+    for (int r = 0; r < n; ++r) {
+        void* base = c->sym;
+        if (r != c->rank) {
+            cudaError_t e = cudaIpcOpenMemHandle(&base, all[r], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                set_error("cudaIpcOpenMemHandle(rank %d) failed: %s (peer access between the GPUs is required)", r, cudaGetErrorString(e));
+                cudaGetLastError();
+                return KSPEC_ERR_UNSUPPORTED;
+            }
+            c->peerMapped[r] = base;
+        }
+        c->px.slots[r] = (double*)base;
+        c->px.flags[r] = (unsigned long long*)((char*)base + dataBytes);
+    }
+    void* small = nullptr;
+    CCK(cudaMalloc(&small, 64));
+    CCK(cudaMemset(small, 0, 64));
+    c->px.counter = (unsigned int*)small;
+    c->px.status = (int*)((char*)small + 32);
+    // nobody may start writing before every rank has mapped everything: one tiny all-reduce as a barrier
+    double* dz = nullptr;
+    CCK(cudaMalloc(&dz, 8));
+    CCK(cudaMemset(dz, 0, 8));
+    NCK(api().AllReduce(dz, dz, 1, ncclDouble, ncclSum, c->comm, c->st));
+    CCK(cudaStreamSynchronize(c->st));
+    cudaFree(dz);
+    return plan_attach_peer(plan, &c->px);
+}
+
+int kspec_comm_peer_status(kspec_comm* c, int* timedOut) {
+    if (!c || !timedOut) { set_error("bad argument"); return KSPEC_ERR_ARG; }
+    *timedOut = 0;
+    if (!c->sym) return KSPEC_OK;
+    DevGuard guard(c->device);
+    CCK(cudaMemcpy(timedOut, c->px.status, sizeof(int), cudaMemcpyDeviceToHost));
+    return KSPEC_OK;
+}
+
 int kspec_comm_finalize(kspec_comm* c) {
     if (!c) return KSPEC_OK;
     DevGuard guard(c->device);
+    if (c->sym) {
+        cudaDeviceSynchronize();         // plans that were attached must not run sharded batches after this point
+        if (c->comm && api().ok) {      // every rank has stopped using the peers' buffers before anything is unmapped or freed
+            double* dz = nullptr;
+            if (cudaMalloc(&dz, 8) == cudaSuccess) {
+                cudaMemset(dz, 0, 8);
+                api().AllReduce(dz, dz, 1, ncclDouble, ncclSum, c->comm, c->st);
+                cudaStreamSynchronize(c->st);
+                cudaFree(dz);
+            }
+        }
+        for (int r = 0; r < KSPEC_MAX_PEERS; ++r) if (c->peerMapped[r]) cudaIpcCloseMemHandle(c->peerMapped[r]);
+        if (c->px.counter) cudaFree(c->px.counter);
+        cudaFree(c->sym);
+        c->sym = nullptr;
+    }
     if (c->st) cudaStreamSynchronize(c->st);
     if (c->comm && api().ok) api().CommDestroy(c->comm);
     if (c->buf) cudaFree(c->buf);

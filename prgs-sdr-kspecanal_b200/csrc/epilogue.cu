@@ -23,7 +23,8 @@ constexpr int FIN_X = 8, FIN_Y = 64;
 template <typename T>
 __global__ void __launch_bounds__(FIN_X * FIN_Y) stats_finish_kernel(const T* __restrict__ wsMax, const T* __restrict__ wsMin, int slots,
                                     const T* __restrict__ avgRows, int avgWin, int F, const double* __restrict__ carry,
-                                    int firstIsSeed, double avgScale, double* __restrict__ out, int partialsLinear, T gain) {
+                                    int firstIsSeed, double avgScale, double* __restrict__ out, int partialsLinear, T gain,
+                                    PeerExchange px, unsigned long long seq) {
     __shared__ double shMax[FIN_Y][FIN_X + 1], shMin[FIN_Y][FIN_X + 1], shAvg[FIN_Y][FIN_X + 1];
     const int j = blockIdx.x * FIN_X + threadIdx.x;
     const bool inb = j < F;
@@ -48,31 +49,93 @@ __global__ void __launch_bounds__(FIN_X * FIN_Y) stats_finish_kernel(const T* __
         }
         __syncthreads();
     }
-    if (threadIdx.y != 0 || !inb) return;
-    mx = shMax[0][threadIdx.x];
-    mn = shMin[0][threadIdx.x];
-    if (partialsLinear) {
-        // the R32 kernels reduce the normalised LINEAR amplitudes (the dB map is monotone): the same conversion as the rows get
-        mx = (double)(to_db((T)mx) - gain);
-        mn = (double)(to_db((T)mn) - gain);
+    if (threadIdx.y == 0 && inb) {
+        mx = shMax[0][threadIdx.x];
+        mn = shMin[0][threadIdx.x];
+        if (partialsLinear) {
+            // the R32 kernels reduce the normalised LINEAR amplitudes (the dB map is monotone): the same conversion as the rows get
+            mx = (double)(to_db((T)mx) - gain);
+            mn = (double)(to_db((T)mn) - gain);
+        }
+        if (carry) {
+            mx = fmax(mx, carry[j]);
+            mn = fmin(mn, carry[F + j]);
+        }
+        double a;
+        int r = 0;
+        if (carry) a = carry[2 * F + j];
+        else if (firstIsSeed) { a = (avgWin <= FIN_Y) ? shAvg[0][threadIdx.x] : (double)avgRows[j]; r = 1; }
+        else a = 0.0;
+        if (avgWin <= FIN_Y) {
+            for (; r < avgWin; ++r) a = (a + shAvg[r][threadIdx.x]) / 2;
+        } else {
+            for (; r < avgWin; ++r) a = (a + (double)avgRows[(int64_t)r * F + j]) / 2;
+        }
+        a = (avgScale == 0.0) ? 0.0 : a * avgScale;
+        out[j] = mx;
+        out[F + j] = mn;
+        out[2 * F + j] = a;
+        // the exchange, folded into this kernel: the three values go straight into slot `rank` of every rank's symmetric buffer
+        // (peer stores over NVLink; the local rank's own copy is one of them)
+        if (px.nRanks > 0) {
+            const size_t ofs = ((size_t)(seq & 1) * px.nRanks + px.rank) * 3 * (size_t)F;
+            for (int r2 = 0; r2 < px.nRanks; ++r2) {
+                double* d = px.slots[r2] + ofs;
+                d[j] = mx;
+                d[F + j] = mn;
+                d[2 * F + j] = a;
+            }
+        }
     }
-    if (carry) {
-        mx = fmax(mx, carry[j]);
-        mn = fmin(mn, carry[F + j]);
+    if (px.nRanks > 0) {
+        // last block done -> every write of this launch is visible system-wide -> raise this rank's flag on every rank
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0 && threadIdx.y == 0) {
+            const unsigned int done = atomicAdd(px.counter, 1u);
+            if (done == gridDim.x - 1) {
+                *px.counter = 0;
+                __threadfence_system();
+                for (int r2 = 0; r2 < px.nRanks; ++r2)
+                    *reinterpret_cast<volatile unsigned long long*>(px.flags[r2] + (seq & 1) * px.nRanks + px.rank) = seq;
+            }
+        }
     }
-    double a;
-    int r = 0;
-    if (carry) a = carry[2 * F + j];
-    else if (firstIsSeed) { a = (avgWin <= FIN_Y) ? shAvg[0][threadIdx.x] : (double)avgRows[j]; r = 1; }
-    else a = 0.0;
-    if (avgWin <= FIN_Y) {
-        for (; r < avgWin; ++r) a = (a + shAvg[r][threadIdx.x]) / 2;
-    } else {
-        for (; r < avgWin; ++r) a = (a + (double)avgRows[(int64_t)r * F + j]) / 2;
+}
+
+// Second half of the peer exchange: wait until every rank's flag of this epoch carries `seq`, then MAX / MIN / SUM over the slots
+// of the LOCAL symmetric buffer (the peers wrote into it).  A rank that never arrives trips a time-out (status = 1) instead of
+// hanging the GPU.
+__global__ void peer_combine_kernel(PeerExchange px, unsigned long long seq, double* __restrict__ out) {
+    __shared__ int ok;
+    const int F = px.F;
+    if (threadIdx.x == 0) {
+        ok = 1;
+        const long long t0 = clock64();
+        for (int r = 0; r < px.nRanks; ++r) {
+            volatile unsigned long long* f = px.flags[px.rank] + (seq & 1) * px.nRanks + r;
+            while (*f < seq) {
+                if (clock64() - t0 > 4000000000LL) { ok = 0; *px.status = 1; break; }      // ~2 s
+                __nanosleep(200);
+            }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (!ok) return;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= F) return;
+    const double* base = px.slots[px.rank] + (size_t)(seq & 1) * px.nRanks * 3 * (size_t)F;
+    double mx = -d_inf(), mn = d_inf(), av = 0.0;
+    for (int r = 0; r < px.nRanks; ++r) {
+        const double* s = base + (size_t)r * 3 * F;
+        mx = fmax(mx, __ldcg(s + j));
+        mn = fmin(mn, __ldcg(s + F + j));
+        av += __ldcg(s + 2 * F + j);                  // rank order: the same sum on every rank
     }
     out[j] = mx;
     out[F + j] = mn;
-    out[2 * F + j] = (avgScale == 0.0) ? 0.0 : a * avgScale;
+    out[2 * F + j] = av;
 }
 
 template <typename T> __global__ void widen_kernel(const T* __restrict__ s, double* __restrict__ d, int64_t n) {
@@ -340,15 +403,21 @@ inline int nblk(int64_t n, int t) { return (int)((n + t - 1) / t); }
 
 void launch_stats_finish(int prec, const void* wsMax, const void* wsMin, int slots, const void* avgRows, int avgWin, int F,
                          const double* carry, int firstIsSeed, double avgScale, double* out, cudaStream_t st, int partialsLinear,
-                         double gain) {
+                         double gain, const PeerExchange* px, unsigned long long seq) {
+    PeerExchange none;
+    const PeerExchange& pe = px ? *px : none;
     if (prec == KSPEC_PREC_F32)
         stats_finish_kernel<float><<<nblk(F, FIN_X), dim3(FIN_X, FIN_Y), 0, st>>>((const float*)wsMax, (const float*)wsMin, slots,
                                                                  (const float*)avgRows, avgWin, F, carry, firstIsSeed, avgScale, out,
-                                                                 partialsLinear, (float)gain);
+                                                                 partialsLinear, (float)gain, pe, seq);
     else
         stats_finish_kernel<double><<<nblk(F, FIN_X), dim3(FIN_X, FIN_Y), 0, st>>>((const double*)wsMax, (const double*)wsMin, slots,
                                                                   (const double*)avgRows, avgWin, F, carry, firstIsSeed, avgScale, out,
-                                                                  partialsLinear, gain);
+                                                                  partialsLinear, gain, pe, seq);
+}
+
+void launch_peer_combine(const PeerExchange& px, unsigned long long seq, double* out, cudaStream_t st) {
+    peer_combine_kernel<<<nblk(px.F, 128), 128, 0, st>>>(px, seq, out);
 }
 
 void launch_widen(int prec, const void* src, double* dst, int64_t n, cudaStream_t st) {

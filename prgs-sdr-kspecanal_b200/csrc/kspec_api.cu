@@ -73,6 +73,7 @@ struct kspec_plan {
     bool frameParallelOff = false; // KSPEC_FRAME_PARALLEL=0 at plan creation
     size_t chunkBytes = (size_t)256 << 20;   // pipelined host batches; KSPEC_PIPELINE_CHUNK_BYTES at plan creation
     int64_t statsSeq = 0;          // bumped by every batch that rewrites `stats` (kspec_comm_join checks it)
+    kspec::PeerExchange* peer = nullptr;   // peer-memory exchange attached by kspec_comm_peer_setup (owned by the communicator)
     bool shardedHint = false;      // the current batch is a shard of a larger capture (scanIndexBase / nScansTotal)
     bool r32Off = false;          // KSPEC_NO_R32=1 at plan creation: keep the 16/16/8 layouts (A/B runs, tests)
     bool r32Pipe = false;         // KSPEC_R32_PIPE=1 at plan creation: the two-role pipeline (curscan_r32p.cuh) instead of the one-role kernel; kiR32 describes it
@@ -301,6 +302,12 @@ std::vector<double> host_lin_twiddles(int log2F) {
         lns += l;
     }
     return out;
+}
+int plan_attach_peer(kspec_plan* pl, PeerExchange* px) {
+    if (!pl) { set_error("null plan"); return KSPEC_ERR_ARG; }
+    if (px && px->F != pl->F) { set_error("peer exchange was set up for fftSize %d, plan has %d", px->F, pl->F); return KSPEC_ERR_ARG; }
+    pl->peer = px;
+    return KSPEC_OK;
 }
 bool plan_stats_view(kspec_plan* pl, double** stats3F, int* F, cudaStream_t* st, int64_t* seq) {
     if (!pl || !pl->haveBatch || !pl->stats.p) return false;
@@ -537,7 +544,7 @@ namespace {
 // offset) and whose row buffers (pl->rows / pl->hm, reserved by the caller for the whole batch) receive this part at row
 // scanOfs.  dCarry: device [max|min|avg] to continue from, or nullptr.  Leaves [max|min|avg] in pl->stats.
 int zerospan_part(kspec_plan* pl, const void* dSamples, int64_t nScans, int64_t scanOfs, double gain, bool haveAdj, int hmMode, int W,
-                  int rowsKind, bool wantHm, const double* dCarry, int firstIsSeed, double avgScale) {
+                  int rowsKind, bool wantHm, const double* dCarry, int firstIsSeed, double avgScale, bool exchange = false) {
     const int F = pl->F;
     const size_t rb = real_bytes(pl->prec);
     int rc;
@@ -553,9 +560,14 @@ int zerospan_part(kspec_plan* pl, const void* dSamples, int64_t nScans, int64_t 
     if (haveAdj) p.adj = pl->adj.p;
     int slots = 0, statsLinear = 0;
     if ((rc = run_engine(pl, p, &slots, &statsLinear))) return rc;
+    // a shard of a multi-GPU capture with the peer exchange attached: the statistics kernel also writes this rank's vectors
+    // into every rank's symmetric buffer, and a small second kernel reduces over the ranks: `stats` then holds Fft.Max/Min/Avg
+    const bool px = exchange && pl->peer && pl->peer->F == F;
+    const unsigned long long seq = px ? ++pl->peer->seq : 0;
     launch_stats_finish(pl->prec, pl->wsMax.p, pl->wsMin.p, slots, pl->avgRows.p, p.avgWin, F, dCarry, firstIsSeed, avgScale,
-                        (double*)pl->stats.p, pl->st, statsLinear, gain);
+                        (double*)pl->stats.p, pl->st, statsLinear, gain, px ? pl->peer : nullptr, seq);
     pl->launches += 1;
+    if (px) { launch_peer_combine(*pl->peer, seq, (double*)pl->stats.p, pl->st); pl->launches += 1; }
     pl->statsSeq += 1;
     CK(cudaGetLastError());
     return KSPEC_OK;
@@ -619,7 +631,7 @@ int kspec_zerospan_batch_dev(kspec_plan* pl, const void* dSamples, int64_t nScan
     if ((rc = zerospan_prepare(pl, nScans, W, rowsKind, wantHm != 0, adj, mx, mn, av, carry))) return rc;
     if ((rc = zerospan_part(pl, dSamples, nScans, 0, gain, adj != nullptr, hmMode, W, rowsKind, wantHm != 0,
                             carry ? (const double*)pl->carry.p : nullptr, (!carry && scanIndexBase == 0) ? 1 : 0,
-                            shard_avg_scale(scanIndexBase, nScans, nScansTotal))))
+                            shard_avg_scale(scanIndexBase, nScans, nScansTotal), /*exchange=*/!carry && nScansTotal != nScans)))
         return rc;
     pl->lastScans = nScans; pl->lastRowsKind = rowsKind; pl->lastW = W; pl->lastHm = wantHm != 0; pl->haveBatch = true;
     return KSPEC_OK;

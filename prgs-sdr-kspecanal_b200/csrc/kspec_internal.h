@@ -70,12 +70,29 @@ constexpr int SMEM_MAX_LOG2F_F64 = 13;
 constexpr int SMEM_MIN_LOG2F = 4;
 constexpr int AVG_WINDOW = 64;   // rows that can still influence the float64 halving average (2^-63 cut-off)
 
+// ---- peer-memory exchange of the per-bin statistics (comm.cu sets it up, epilogue.cu uses it) ---------------------------------
+// Every rank owns a "symmetric" buffer: two epochs x nRanks slots x 3F float64 + two epochs x nRanks flags.  stats_finish_kernel
+// writes this rank's [max | min | pre-weighted avg] into slot `rank` of EVERY rank's buffer (stores over NVLink through CUDA IPC
+// mappings), and its last block raises flag `rank` on every rank; peer_combine_kernel waits for all flags of the epoch and reduces
+// MAX / MIN / SUM over the slots of the local buffer: the exchange is the tail of the compute kernel, no collective library call.
+constexpr int KSPEC_MAX_PEERS = 8;
+struct PeerExchange {
+    int nRanks = 0, rank = 0, F = 0;
+    double* slots[KSPEC_MAX_PEERS] = {};             // base of every rank's symmetric buffer, as mapped into THIS process
+    unsigned long long* flags[KSPEC_MAX_PEERS] = {}; // flag arrays inside those buffers
+    unsigned int* counter = nullptr;                 // local: blocks of stats_finish_kernel that have finished (last one raises the flags)
+    int* status = nullptr;                           // local: set to 1 by peer_combine_kernel on a wait time-out
+    unsigned long long seq = 0;                      // exchanges issued so far (epoch = seq & 1)
+};
+void launch_peer_combine(const PeerExchange& px, unsigned long long seq, double* out /*3F, local stats overwritten by the reduction*/, cudaStream_t st);
+
 // ---- epilogue.cu -------------------------------------------------------------------------------------------------
 // Max/Min over the per-team partials (+ carry), Avg recurrence over the last rows (+ carry), scaled for sharding.
 void launch_stats_finish(int prec, const void* wsMax, const void* wsMin, int slots, const void* avgRows, int avgWin,
                          int F, const double* carry /*3F or null*/, int firstIsSeed, double avgScale,
                          double* out /*3F*/, cudaStream_t st, int partialsLinear = 0 /*partials hold linear amplitudes*/,
-                         double gain = 0.0);
+                         double gain = 0.0, const PeerExchange* px = nullptr /*also write `out` into every rank's slot*/,
+                         unsigned long long seq = 0);
 // T -> float64 widening of result rows
 void launch_widen(int prec, const void* src, double* dst, int64_t n, cudaStream_t st);
 // float64 host-side vectors -> T
@@ -126,5 +143,7 @@ void set_error(const char* fmt, ...);
 
 // comm.cu <- kspec_api.cu: device view of the [max | min | avg] vectors the last zeroSpan batch left in the plan
 bool plan_stats_view(kspec_plan* plan, double** stats3F, int* F, cudaStream_t* st, int64_t* seq = nullptr);
+// comm.cu -> kspec_api.cu: attach / detach the peer-memory exchange to a plan (sharded zeroSpan batches then leave REDUCED statistics)
+int plan_attach_peer(kspec_plan* plan, PeerExchange* px);
 
 }  // namespace kspec

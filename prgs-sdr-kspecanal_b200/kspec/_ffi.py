@@ -88,6 +88,8 @@ SIGNATURES = {
     "kspec_comm_allreduce_plan": (C.c_int, [_P, _P]),
     "kspec_comm_join": (C.c_int, [_P, _P]),
     "kspec_comm_fetch_reduced": (C.c_int, [_P, _D, _D, _D, _I64]),
+    "kspec_comm_peer_setup": (C.c_int, [_P, _P]),
+    "kspec_comm_peer_status": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "kspec_comm_finalize": (C.c_int, [_P]),
 }
 

@@ -54,6 +54,16 @@ class Comm:
         check(_ffi.lib().kspec_comm_fetch_reduced(self._h, dptr(mx), dptr(mn), dptr(av), int(n)))
         return mx, mn, av
 
+    def peer_setup(self, plan):
+        """collective: fold the exchange into the plan's statistics kernel (peer-memory writes over NVLink, kspec_comm_peer_setup):
+        every sharded zerospan_batch_dev of ``plan`` then leaves the statistics of the whole capture in the plan"""
+        check(_ffi.lib().kspec_comm_peer_setup(self._h, plan._h))
+
+    def peer_timed_out(self):
+        t = C.c_int(0)
+        check(_ffi.lib().kspec_comm_peer_status(self._h, C.byref(t)))
+        return bool(t.value)
+
     def close(self):
         if self._h is not None and self._h.value:
             _ffi.lib().kspec_comm_finalize(self._h)

@@ -63,6 +63,22 @@ def _worker(rank, world, uid_path, q):
         plan.dev_free(d)
         local_half = plan.zerospan_batch(x[a * S:(a + half) * S], half, GAIN, XRES, "MAX")
         overl_ok = bool(refused and np.array_equal(nxt["max"], local_half["max"]) and np.array_equal(nxt["avg"], local_half["avg"]))
+    # the exchange folded into the statistics kernel: peer-memory writes over NVLink (kspec_comm_peer_setup), three batches in
+    # a row (both epochs of the symmetric buffer get reused), float64 and float32 plans
+    peer_ok = True
+    for prec in ("f64", "f32"):
+        with Plan(F, S, R, np.hanning(F), "AVG", precision=prec, device=rank) as plan:
+            comm.peer_setup(plan)
+            d = plan.dev_alloc((b - a) * S * 8)
+            plan.dev_upload(d, x[a * S:b * S])
+            for _ in range(3):
+                plan.zerospan_batch_dev(d, b - a, GAIN, XRES, "MAX", scan_index_base=a, n_scans_total=N)
+                got = plan.zerospan_fetch()
+            plan.dev_free(d)
+            one = plan.zerospan_batch(x, N, GAIN, XRES, "MAX")            # not a shard: no exchange, this rank alone
+            peer_ok = peer_ok and np.array_equal(got["max"], one["max"]) and np.array_equal(got["min"], one["min"])
+            peer_ok = peer_ok and float(np.max(np.abs(got["avg"] - one["avg"]))) < (1e-9 if prec == "f64" else 1e-4)
+    peer_ok = bool(peer_ok and not comm.peer_timed_out())
     # stepped scan sharded by frequency step: SUM of the stitch partials over NVLink
     from oracle import kspec_oracle as O
     Fs, rs = 64, 0.1
@@ -79,7 +95,7 @@ def _worker(rank, world, uid_path, q):
         plan.scan_stats_update(cur, steps[-1]["i_done"], 0, st)
     comm.close()
     q.put((rank, out["max"], out["min"], out["avg"], dev["max"], dev["min"], dev["avg"], st["cur"], st["max"], st["avg"],
-           red[0], red[1], red[2], overl_ok))
+           red[0], red[1], red[2], overl_ok, peer_ok))
 
 
 @pytest.mark.skipif(device_count() < 2, reason="needs two GPUs")
@@ -108,6 +124,7 @@ def test_two_gpu_shards_match_single_gpu(tmp_path):
     sref = O.scan_pass(lin, [True] * len(steps), geo, 19.1, O.scan_init_state(total, 19.1), 0)
     for r in res:
         assert r[13], "overlapped order: join must refuse and leave the plan's batch k+1 statistics alone"
+        assert r[14], "peer-memory exchange: the sharded batches must leave the statistics of the whole capture on every rank"
         for got in (r[1:4], r[4:7], r[10:13]):
             assert np.array_equal(got[0], ref["max"]) and np.array_equal(got[1], ref["min"])
             assert np.max(np.abs(got[2] - ref["avg"])) < 1e-9
