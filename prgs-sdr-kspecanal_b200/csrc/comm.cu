@@ -6,6 +6,7 @@
 #include "kspec_internal.h"
 #include <dlfcn.h>
 #include <nccl.h>
+#include <stdio.h>
 #include <string.h>
 #include <new>
 #include <vector>
@@ -295,14 +296,17 @@ int kspec_comm_peer_setup(kspec_comm* c, kspec_plan* plan) {
     cudaFree(dH);
     c->px = PeerExchange();
     c->px.nRanks = n; c->px.rank = c->rank; c->px.F = F;
+    bool failed = false;
+    char why[160] = "";
     for (int r = 0; r < n; ++r) {
         void* base = c->sym;
         if (r != c->rank) {
             cudaError_t e = cudaIpcOpenMemHandle(&base, all[r], cudaIpcMemLazyEnablePeerAccess);
             if (e != cudaSuccess) {
-                set_error("cudaIpcOpenMemHandle(rank %d) failed: %s (peer access between the GPUs is required)", r, cudaGetErrorString(e));
+                snprintf(why, sizeof(why), "cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
                 cudaGetLastError();
-                return KSPEC_ERR_UNSUPPORTED;
+                failed = true;
+                base = nullptr;
             }
             c->peerMapped[r] = base;
         }
@@ -314,13 +318,26 @@ int kspec_comm_peer_setup(kspec_comm* c, kspec_plan* plan) {
     CCK(cudaMemset(small, 0, 64));
     c->px.counter = (unsigned int*)small;
     c->px.status = (int*)((char*)small + 32);
-    // nobody may start writing before every rank has mapped everything: one tiny all-reduce as a barrier
+    // nobody may start writing before every rank has mapped everything, and every rank must learn whether ANY rank failed (a
+    // rank that left early would leave the others waiting in their first exchange): one tiny all-reduce as barrier + vote
     double* dz = nullptr;
     CCK(cudaMalloc(&dz, 8));
-    CCK(cudaMemset(dz, 0, 8));
+    const double vote = failed ? 1.0 : 0.0;
+    CCK(cudaMemcpyAsync(dz, &vote, 8, cudaMemcpyHostToDevice, c->st));
     NCK(api().AllReduce(dz, dz, 1, ncclDouble, ncclSum, c->comm, c->st));
+    double votes = 0.0;
+    CCK(cudaMemcpyAsync(&votes, dz, 8, cudaMemcpyDeviceToHost, c->st));
     CCK(cudaStreamSynchronize(c->st));
     cudaFree(dz);
+    if (votes > 0.0) {
+        for (int r = 0; r < KSPEC_MAX_PEERS; ++r) if (c->peerMapped[r]) { cudaIpcCloseMemHandle(c->peerMapped[r]); c->peerMapped[r] = nullptr; }
+        cudaFree(small);
+        cudaFree(c->sym);
+        c->sym = nullptr;
+        c->px = PeerExchange();
+        set_error("peer exchange unavailable (%s): peer access between the GPUs is required; use kspec_comm_allreduce_*", failed ? why : "a peer rank could not map the buffers");
+        return KSPEC_ERR_UNSUPPORTED;
+    }
     return plan_attach_peer(plan, &c->px);
 }
 

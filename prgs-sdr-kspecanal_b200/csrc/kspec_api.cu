@@ -199,7 +199,8 @@ int run_engine(kspec_plan* pl, ScanParams& p, int* slotsOut, int* statsLinear = 
             }
         }
         // large batches of the headline shape run several independent teams per CTA (one CTA per SM); small ones the base layout
-        const bool r32 = pl->kiR32.ctasPerSm > 0 && !pl->r32Off && nFrames <= 1024 && p.nScans >= (int64_t)2 * pl->smCount * pl->kiR32.teams;
+        const bool r32 = pl->kiR32.ctasPerSm > 0 && !pl->r32Off && nFrames <= 1024 && p.nScans < (int64_t)INT32_MAX / 2 &&
+                         p.nScans >= (int64_t)2 * pl->smCount * pl->kiR32.teams;
         const bool multi = !r32 && pl->kiMulti.ctasPerSm > 0 && p.nScans >= (int64_t)2 * pl->smCount * pl->kiMulti.teams;
         const SmemKernelInfo& ki = r32 ? pl->kiR32 : (multi ? pl->kiMulti : pl->ki);
         const int variant = multi ? SMEM_VARIANT_MULTI : SMEM_VARIANT_BASE;

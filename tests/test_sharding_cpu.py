@@ -103,3 +103,29 @@ def test_two_process_gloo_allreduce_matches_single_process():
     for _, mx, mn, av in res:
         assert np.allclose(mx, ref["max"], atol=1e-9) and np.allclose(mn, ref["min"], atol=1e-9)
         assert np.allclose(av, ref["avg"], atol=1e-9)
+
+
+def test_uncovered_bins_keep_the_previous_cur():
+    """kspec_scan_shard writes 0 into bins that no step covers; after the SUM over shards the caller restores the previous
+    Fft.Cur there, which is what the single-plan stitch (K:643-650 never touches such bins) leaves behind"""
+    from kspec.sharding import keep_uncovered, scan_cover
+    F, total = 8, 40
+    i_start = [0, 4, 8, 12]                               # covers bins [0, 20): 20..39 are never written
+    prev = np.arange(total, dtype=np.float64) - 100.0
+    summed = np.where(np.arange(total) < 20, 7.0, 0.0)
+    out = keep_uncovered(summed, prev, i_start, F)
+    assert np.array_equal(out[:20], summed[:20]) and np.array_equal(out[20:], prev[20:])
+    i0, i1 = scan_cover(i_start, F, total)
+    assert (i0[:20] <= i1[:20]).all() and (i0[20:] > i1[20:]).all()
+
+
+def test_bdata_switches_gate_what_reaches_the_dict():
+    """bDataMax / bDataMin / bDataAvg (K:471-476): the batch always computes all three (they are carried between batches), the
+    switches decide which of them are published in d['Fft.*']"""
+    from kspec import hotpath
+    d = {"bDataMax": True, "bDataMin": False, "bDataAvg": True, "Fft.Max": None, "Fft.Min": None, "Fft.Avg": None}
+    out = {"max": np.ones(4), "min": -np.ones(4), "avg": np.zeros(4)}
+    hotpath._publish_stats(d, out)
+    assert d["Fft.Max"] is out["max"] and d["Fft.Avg"] is out["avg"] and d["Fft.Min"] is None
+    st = hotpath._carried_state(d)
+    assert st[0] is out["max"] and st[1] is out["min"] and st[2] is out["avg"]
