@@ -268,15 +268,9 @@ int kspec_comm_peer_setup(kspec_comm* c, kspec_plan* plan) {
         // buffers and the sequence, so their sharded batches must be issued in the same order on every rank)
         return plan_attach_peer(plan, &c->px);
     }
-    double* stats = nullptr;
-    int F = 0;
-    cudaStream_t pst = nullptr;
-    {   // fftSize of the plan (plan_stats_view needs a batch; kspec_plan_info does not)
-        kspec_plan_info_t info;
-        if (kspec_plan_info(plan, &info) != KSPEC_OK) return KSPEC_ERR_ARG;
-        F = info.fft_size;
-        (void)stats; (void)pst;
-    }
+    kspec_plan_info_t info;
+    if (kspec_plan_info(plan, &info) != KSPEC_OK) return KSPEC_ERR_ARG;
+    const int F = info.fft_size;
     const int n = c->nRanks;
     const size_t dataBytes = (size_t)2 * n * 3 * F * 8, flagBytes = (size_t)2 * n * 8;
     const size_t total = dataBytes + flagBytes + 256;
