@@ -142,6 +142,53 @@ template <typename T> __device__ __forceinline__ T pos_inf();
 template <> __device__ __forceinline__ float pos_inf<float>() { return __int_as_float(0x7f800000); }
 template <> __device__ __forceinline__ double pos_inf<double>() { return __longlong_as_double(0x7ff0000000000000LL); }
 
+// Max / Min of non-negative values as integer reductions in L2 (no return value, hence no load latency): the normalised amplitudes
+// are >= 0, where IEEE order is signed-integer order on the bit patterns.  The slot is initialised by a plain store.
+__device__ __forceinline__ void red_max_nonneg(float* p, float v) { asm volatile("red.global.max.s32 [%0], %1;" ::"l"(p), "r"(__float_as_int(v)) : "memory"); }
+__device__ __forceinline__ void red_min_nonneg(float* p, float v) { asm volatile("red.global.min.s32 [%0], %1;" ::"l"(p), "r"(__float_as_int(v)) : "memory"); }
+__device__ __forceinline__ void red_max_nonneg(double* p, double v) { asm volatile("red.global.max.s64 [%0], %1;" ::"l"(p), "l"(__double_as_longlong(v)) : "memory"); }
+__device__ __forceinline__ void red_min_nonneg(double* p, double v) { asm volatile("red.global.min.s64 [%0], %1;" ::"l"(p), "l"(__double_as_longlong(v)) : "memory"); }
+
+// Per-scan outputs from the normalised, fftshift-ed linear row in shared memory (erow[F]): thread tid walks the positions
+// tid + NT i in a ROLLED loop (compact code: the unrolled form was a third of the kernel and evicted the frame loop from the
+// instruction cache) with coalesced global accesses.  data_proc K:100-112, zero_span K:469-478.  The running Max/Min of this
+// team (K:471-474) are kept as LINEAR amplitudes (10 log10 is monotone; stats_finish_kernel converts them exactly as the rows are
+// converted here) and updated by fire-and-forget reductions.  Leaves dB - adj in erow for the waterfall compress.
+template <typename T, int NT, int F>
+__device__ __forceinline__ void smem_epilogue_rows(const ScanParams& p, T* erow, int64_t scan, bool valid, int64_t it, int slot, int tid) {
+    T* __restrict__ rows = reinterpret_cast<T*>(p.rows);
+    const bool needDb = (p.rowsKind == KSPEC_ROWS_DB) || p.wantStats || (p.hm != nullptr);
+    const bool needRow = (p.hm != nullptr);
+    T* __restrict__ wmax = reinterpret_cast<T*>(p.wsMax) + (int64_t)slot * F;
+    T* __restrict__ wmin = reinterpret_cast<T*>(p.wsMin) + (int64_t)slot * F;
+    const T gain = (T)p.gain, minAmp = (T)p.minAmp;
+    const T* __restrict__ adj = reinterpret_cast<const T*>(p.adj);
+    const int64_t ar = scan - (p.nScans - p.avgWin);
+    T* __restrict__ avgRow = (valid && ar >= 0 && p.wantStats) ? reinterpret_cast<T*>(p.avgRows) + ar * F : nullptr;
+#pragma unroll 4
+    for (int jj = tid; jj < F; jj += NT) {
+        T lin = erow[jj];
+        if (valid && p.rowsKind == KSPEC_ROWS_LINEAR) rows[scan * F + jj] = lin;
+        if (needDb) {
+            if (p.dbClip) lin = fmax(lin, minAmp);
+            T db = to_db(lin) - gain;
+            if (p.infToZero && isinf(db)) db = (T)0;
+            if (valid && p.rowsKind == KSPEC_ROWS_DB) rows[scan * F + jj] = db;
+            if (p.wantStats) {
+                if (it == 0) {
+                    wmax[jj] = valid ? lin : (T)0;                 // idle team: identities of max / min over amplitudes
+                    wmin[jj] = valid ? lin : pos_inf<T>();
+                } else if (valid) {
+                    red_max_nonneg(&wmax[jj], lin);
+                    red_min_nonneg(&wmin[jj], lin);
+                }
+                if (avgRow) avgRow[jj] = db;
+            }
+            if (needRow) erow[jj] = adj ? db - adj[jj] : db;
+        }
+    }
+}
+
 // VB ("virtual bases"): the frame-parallel form for small batches.  Every frame of every scan is launched as a one-frame
 // scan of its own whose first sample comes from the table p.scanBase (= scan*fullSize + frame offset), so that a single
 // scan of 15..71 frames spreads over as many teams instead of walking its frames on one; frames_combine_kernel
@@ -312,48 +359,15 @@ curscan_smem_kernel(const ScanParams p) {
         }
 
         // ---------------- per-scan epilogue: thread owns bins k = tid + NT*m, shifted position j = k ^ F/2 -------------
-        T* __restrict__ rows = reinterpret_cast<T*>(p.rows);
-        const bool needDb = (p.rowsKind == KSPEC_ROWS_DB) || p.wantStats || (p.hm != nullptr);
+        // the normalised row goes through shared memory (bufA: the buffer the last exchange did NOT use, see above) in
+        // fftshift-ed order; smem_epilogue_rows walks it by position
         const bool needRow = (p.hm != nullptr);
-        // scratch row for the waterfall compress: bufA, the buffer the last exchange did NOT use (see above)
         T* erow = reinterpret_cast<T*>(bufA);
-        if (needRow && !C::DBUF) sync();
-        // running Max/Min of this team (K:471-474): fetch all partials in one batch so the loads overlap the dB math
-        T* __restrict__ wmax = reinterpret_cast<T*>(p.wsMax) + (int64_t)slot * F;
-        T* __restrict__ wmin = reinterpret_cast<T*>(p.wsMin) + (int64_t)slot * F;
-        T omax[P], omin[P];
-        if (p.wantStats && it > 0) {
+        if (!C::DBUF) sync();
 #pragma unroll
-            for (int m = 0; m < P; ++m) {
-                const int j = (tid + NT * m) ^ (F >> 1);
-                omax[m] = wmax[j];
-                omin[m] = wmin[j];
-            }
-        }
-#pragma unroll
-        for (int m = 0; m < P; ++m) {
-            const int j = (tid + NT * m) ^ (F >> 1);
-            T lin = acc[m] * linScale;
-            if (valid && p.rowsKind == KSPEC_ROWS_LINEAR) rows[scan * F + j] = lin;
-            if (needDb) {
-                if (p.dbClip) lin = fmax(lin, (T)p.minAmp);
-                T db = to_db(lin) - (T)p.gain;
-                if (p.infToZero && isinf(db)) db = (T)0;
-                if (valid && p.rowsKind == KSPEC_ROWS_DB) rows[scan * F + j] = db;
-                if (p.wantStats) {
-                    if (it == 0) {
-                        wmax[j] = valid ? db : -pos_inf<T>();
-                        wmin[j] = valid ? db : pos_inf<T>();
-                    } else if (valid) {
-                        wmax[j] = fmax(omax[m], db);
-                        wmin[j] = fmin(omin[m], db);
-                    }
-                    const int64_t ar = scan - (p.nScans - p.avgWin);
-                    if (valid && ar >= 0) reinterpret_cast<T*>(p.avgRows)[ar * F + j] = db;
-                }
-                if (needRow) erow[j] = p.adj ? db - reinterpret_cast<const T*>(p.adj)[j] : db;
-            }
-        }
+        for (int m = 0; m < P; ++m) erow[(tid + NT * m) ^ (F >> 1)] = acc[m] * linScale;
+        sync();
+        smem_epilogue_rows<T, NT, F>(p, erow, scan, valid, it, slot, tid);
         if (needRow) {
             sync();
             // _data_plotcompress (K:184-200): W groups of g adjacent bins
@@ -372,8 +386,8 @@ curscan_smem_kernel(const ScanParams p) {
                 }
                 if (valid) hm[scan * W + w] = r;
             }
-            sync();
         }
+        sync();                                                  // the scratch row is an exchange buffer of the next frame
     }
 }
 

@@ -247,7 +247,7 @@ int run_engine(kspec_plan* pl, ScanParams& p, int* slotsOut, int* statsLinear = 
         if (e != 0) { set_error("scan kernel launch failed: %s", cudaGetErrorString((cudaError_t)e)); return KSPEC_ERR_CUDA; }
         pl->launches += 1;
         *slotsOut = slots;
-        if (statsLinear) *statsLinear = r32 ? 1 : 0;          // the R32 kernels keep their Max/Min partials in the linear domain
+        if (statsLinear) *statsLinear = 1;                    // the fused batch kernels keep their Max/Min partials in the linear domain
         return KSPEC_OK;
     }
     // big engines: un-normalised accumulation rows, then a shared epilogue
