@@ -280,6 +280,26 @@ __global__ void linear_epilogue_kernel(const ScanParams p, const T* __restrict__
     }
 }
 
+// the same per-row work without the cross-scan statistics (stepped scans: clip, dB, inf -> 0 only; K:640-641): one thread per
+// (scan, bin), so that many short rows -- 1226 steps of 64 bins in quickFullScan -- do not serialise behind 64 threads
+template <typename T>
+__global__ void linear_rows_kernel(const ScanParams p, const T* __restrict__ acc, int F) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.nScans * F) return;
+    const int64_t s = i / F;
+    const int j = (int)(i - s * F);
+    const int c2 = (F + 1) / 2;
+    const int srcBin = p.accShifted ? j : (j + c2) % F;
+    const int src = p.accL1 ? (((srcBin & ((1 << p.accL1) - 1)) << p.accL2) + (srcBin >> p.accL1)) : srcBin;
+    T lin = acc[s * F + src] * (T)p.linScale;
+    T* rows = reinterpret_cast<T*>(p.rows);
+    if (p.rowsKind == KSPEC_ROWS_LINEAR) { rows[i] = lin; return; }
+    if (p.dbClip) lin = fmax(lin, (T)p.minAmp);
+    T db = db_of(lin) - (T)p.gain;
+    if (p.infToZero && isinf(db)) db = (T)0;
+    rows[i] = db;
+}
+
 // waterfall rows for the linear engines: block per (scan, output column)
 template <typename T>
 __global__ void linear_hm_kernel(const ScanParams p, const T* __restrict__ acc, int F) {
@@ -500,12 +520,18 @@ void launch_frames_combine(int prec, const void* rows, void* out, int64_t nScans
 
 void launch_linear_epilogue(int prec, const ScanParams& p, const void* acc, int F, int slots, cudaStream_t st) {
     (void)slots;
-    if (prec == KSPEC_PREC_F32) {
+    if (!p.wantStats && p.rowsKind != KSPEC_ROWS_NONE) {
+        const unsigned g = nblk(p.nScans * F, 256);
+        if (prec == KSPEC_PREC_F32) linear_rows_kernel<float><<<g, 256, 0, st>>>(p, (const float*)acc, F);
+        else linear_rows_kernel<double><<<g, 256, 0, st>>>(p, (const double*)acc, F);
+    } else if (prec == KSPEC_PREC_F32) {
         linear_epilogue_kernel<float><<<nblk(F, 256), 256, 0, st>>>(p, (const float*)acc, F);
-        if (p.hm) linear_hm_kernel<float><<<(unsigned)(p.nScans * p.hmW), 256, 0, st>>>(p, (const float*)acc, F);
     } else {
         linear_epilogue_kernel<double><<<nblk(F, 256), 256, 0, st>>>(p, (const double*)acc, F);
-        if (p.hm) linear_hm_kernel<double><<<(unsigned)(p.nScans * p.hmW), 256, 0, st>>>(p, (const double*)acc, F);
+    }
+    if (p.hm) {
+        if (prec == KSPEC_PREC_F32) linear_hm_kernel<float><<<(unsigned)(p.nScans * p.hmW), 256, 0, st>>>(p, (const float*)acc, F);
+        else linear_hm_kernel<double><<<(unsigned)(p.nScans * p.hmW), 256, 0, st>>>(p, (const double*)acc, F);
     }
 }
 

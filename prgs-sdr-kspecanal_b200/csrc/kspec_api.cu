@@ -93,6 +93,9 @@ struct kspec_plan {
     // grow-only workspaces
     DevBuf in, rows, hm, wsMax, wsMin, avgRows, adj, adj64, carry, stats, wide, acc, l2, misc, frameRows, vbase, scanState, scanGeo, sched;
     int64_t scanTotal = 0;                         // entries of the device-resident stepped-scan state (0: none)
+    std::vector<int64_t> geoStart, geoDone;        // step geometry currently on the device (kspec_scan_pass re-uploads it only when it changes)
+    std::vector<uint8_t> geoOk;
+    bool geoHasOk = false;
     int64_t vbaseScans = 0;                        // scans covered by the frame-parallel base table in vbase
     // what the last *_dev batch left behind (for fetch)
     int64_t lastScans = 0;
@@ -151,8 +154,11 @@ int run_engine(kspec_plan* pl, ScanParams& p, int* slotsOut, int* statsLinear = 
             const int64_t teamsAvail = (int64_t)pl->smCount * (pl->ki.ctasPerSm > 0 ? pl->ki.ctasPerSm : 1) * pl->ki.teams;
             const int64_t nv = p.nScans * nFrames;
             const bool off = pl->frameParallelOff;                 // always walk the frames of a scan on one team
-            // (up to 64 scans: the per-scan epilogue that follows walks the scans of a batch in order, one thread per bin)
-            if (!off && nFrames > 1 && p.nScans <= 64 && p.nScans * 2 <= teamsAvail && (size_t)nv * pl->F * rb <= ((size_t)256 << 20)) {
+            // (with statistics: up to 64 scans, because the per-scan epilogue that follows then walks the scans of a batch in order,
+            // one thread per bin; rows only -- the stepped scans -- any count that leaves teams idle: 1226 steps of 71 64-point
+            // frames are 87 046 one-frame scans instead of 1226 teams that each walk 71 frames in sequence)
+            const bool fewScans = p.nScans <= 64 || (!p.wantStats && p.hm == nullptr && p.rowsKind != KSPEC_ROWS_NONE);
+            if (!off && nFrames > 1 && fewScans && p.nScans * 2 <= teamsAvail && (size_t)nv * pl->F * rb <= ((size_t)256 << 20)) {
                 int rc;
                 if (pl->vbaseScans < p.nScans) {
                     int64_t cap = 64;
@@ -924,9 +930,21 @@ int scan_pass_common(kspec_plan* pl, const void* samples, bool onDevice, int nSt
     int64_t* dStart = (int64_t*)pl->scanGeo.p;
     int64_t* dDone = dStart + nSteps;
     uint8_t* dOk = (uint8_t*)(dDone + nSteps);
-    CK(cudaMemcpyAsync(dStart, iStart, (size_t)nSteps * 8, cudaMemcpyHostToDevice, pl->st));
-    CK(cudaMemcpyAsync(dDone, iDone, (size_t)nSteps * 8, cudaMemcpyHostToDevice, pl->st));
-    if (stepOk) CK(cudaMemcpyAsync(dOk, stepOk, (size_t)nSteps, cudaMemcpyHostToDevice, pl->st));
+    // the geometry of a stepped scan is the same on every pass (scan_range's loop, K:719-732): three small pageable uploads per
+    // pass were a third of a quickFullScan pass
+    const bool sameGeo = (int)pl->geoStart.size() == nSteps && memcmp(pl->geoStart.data(), iStart, (size_t)nSteps * 8) == 0 &&
+                         memcmp(pl->geoDone.data(), iDone, (size_t)nSteps * 8) == 0 && pl->geoHasOk == (stepOk != nullptr) &&
+                         (!stepOk || memcmp(pl->geoOk.data(), stepOk, (size_t)nSteps) == 0);
+    if (!sameGeo) {
+        pl->geoStart.assign(iStart, iStart + nSteps);
+        pl->geoDone.assign(iDone, iDone + nSteps);
+        pl->geoHasOk = stepOk != nullptr;
+        if (stepOk) pl->geoOk.assign(stepOk, stepOk + nSteps); else pl->geoOk.clear();
+        // the vectors in the plan outlive the asynchronous copies
+        CK(cudaMemcpyAsync(dStart, pl->geoStart.data(), (size_t)nSteps * 8, cudaMemcpyHostToDevice, pl->st));
+        CK(cudaMemcpyAsync(dDone, pl->geoDone.data(), (size_t)nSteps * 8, cudaMemcpyHostToDevice, pl->st));
+        if (stepOk) CK(cudaMemcpyAsync(dOk, pl->geoOk.data(), (size_t)nSteps, cudaMemcpyHostToDevice, pl->st));
+    }
 
     auto engine = [&](const void* dSamples, int first, int count) -> int {
         ScanParams p = base_params(pl, dSamples, count);
