@@ -9,6 +9,7 @@
 #include "bigfft_kernels.cuh"
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace kspec {
@@ -55,6 +56,8 @@ struct BigFft {
     cd *dTwM = nullptr, *dTw1 = nullptr, *dTw2 = nullptr, *dChirp = nullptr, *dV = nullptr, *dZ = nullptr, *dP = nullptr;
     int64_t* dOffs = nullptr;
     int nOffs = 0;
+    bool rowsOcc3 = false;      // last row pass with three CTAs per SM (KSPEC_ROWS_OCC3=1)
+    bool tiledCols = false;     // four-step column pass through shared-memory tiles (cols_tiled_kernel)
     cd* dPw = nullptr;          // Bluestein: product slabs, one per frame of a chunk (dP is the single slab used at plan time)
     size_t zCap = 0;            // bytes allocated for dZ (and dPw)
 };
@@ -109,6 +112,12 @@ BigFft* bigfft_create(int prec, int inFmt, int64_t F, int path, int64_t* convSiz
         }
     }
     *convSize = path == KSPEC_PATH_BLUESTEIN ? b->M : 0;
+    {   // KSPEC_FOURSTEP_TILED=0 keeps the element-wise column pass (A/B measurements); read once, here
+        const char* e = getenv("KSPEC_FOURSTEP_TILED");
+        const char* o = getenv("KSPEC_ROWS_OCC3");
+        b->rowsOcc3 = o && o[0] == '1';
+        b->tiledCols = path == KSPEC_PATH_FOURSTEP && b->l1 >= COLS_TILED_MIN_L && b->l1 <= COLS_TILED_MAX_L && !(e && e[0] == '0');
+    }
     const int64_t M = b->M;
     BCK(cudaMalloc(&b->dWin, (size_t)F * 8));
     BCK(cudaMemcpyAsync(b->dWin, window, (size_t)F * 8, cudaMemcpyHostToDevice, st));
@@ -212,13 +221,16 @@ int bigfft_run(BigFft* b, const void* samples, int64_t scanStride, int64_t nScan
         // pass 1: columns of every (zero padded) frame of the chunk
         if (b->inFmt == KSPEC_IN_U8_IQ) {
             OpColsIn<KSPEC_IN_U8_IQ, false> op{g, smp, scanStride, b->dOffs, nFrames, b->dWin, blue ? b->dChirp : nullptr, b->dTwM, b->dZ, b->u8off, b->u8scale};
-            e = big_cols_in(b->inFmt, blue ? 1 : 0, b->l1, &op, b->dTw1, nfs * L2, b->smCount, st);
+            e = b->tiledCols ? big_cols_tiled(b->inFmt, b->l1, &op, b->dTw1, nfs, b->smCount, st)
+                             : big_cols_in(b->inFmt, blue ? 1 : 0, b->l1, &op, b->dTw1, nfs * L2, b->smCount, st);
         } else if (b->inFmt == KSPEC_IN_C64) {
             OpColsIn<KSPEC_IN_C64, false> op{g, smp, scanStride, b->dOffs, nFrames, b->dWin, blue ? b->dChirp : nullptr, b->dTwM, b->dZ, b->u8off, b->u8scale};
-            e = big_cols_in(b->inFmt, blue ? 1 : 0, b->l1, &op, b->dTw1, nfs * L2, b->smCount, st);
+            e = b->tiledCols ? big_cols_tiled(b->inFmt, b->l1, &op, b->dTw1, nfs, b->smCount, st)
+                             : big_cols_in(b->inFmt, blue ? 1 : 0, b->l1, &op, b->dTw1, nfs * L2, b->smCount, st);
         } else {
             OpColsIn<KSPEC_IN_C128, false> op{g, smp, scanStride, b->dOffs, nFrames, b->dWin, blue ? b->dChirp : nullptr, b->dTwM, b->dZ, b->u8off, b->u8scale};
-            e = big_cols_in(b->inFmt, blue ? 1 : 0, b->l1, &op, b->dTw1, nfs * L2, b->smCount, st);
+            e = b->tiledCols ? big_cols_tiled(b->inFmt, b->l1, &op, b->dTw1, nfs, b->smCount, st)
+                             : big_cols_in(b->inFmt, blue ? 1 : 0, b->l1, &op, b->dTw1, nfs * L2, b->smCount, st);
         }
         *launches += 1;
         if (e) break;
@@ -233,7 +245,7 @@ int bigfft_run(BigFft* b, const void* samples, int64_t scanStride, int64_t nScan
         }
         // last pass: rows, |X|, cumulate over the frames of each scan in registers
         RowsAccParams ra{g, b->dZ, dAcc + s0 * b->F, blue ? 1.0 / (double)b->M : 1.0, cumuMode, nFrames, blue ? 0 : 1};
-        e = big_rows_acc(b->l2, ra, b->dTw2, ns * L1, b->smCount, st);
+        e = big_rows_acc(b->l2, b->rowsOcc3 ? 1 : 0, ra, b->dTw2, ns * L1, b->smCount, st);
         *launches += 1;
     }
     if (e) { set_error("multi-pass FFT launch failed: %s", cudaGetErrorString((cudaError_t)e)); return KSPEC_ERR_CUDA; }

@@ -164,6 +164,123 @@ static int launch_team_fft(const Op& op, const cd* tw, int64_t nBatch, int smCou
     return (int)cudaGetLastError();
 }
 
+// ---- column pass of the four-step transform, tiled ------------------------------------------------------------------
+// team_fft_kernel<OpColsIn> reads a column element by element: the lanes of a warp hold rows e, e+1, ... of ONE column, so every
+// sample, window value, twiddle and Z element of a warp request lies in its own 32-byte sector (stride L2 elements) and the L1
+// tag stage, not HBM, sets the pace (profiles/r2_ncu_fourstep.txt: l1tex 74 %, DRAM 1.2 TB/s).  Here a CTA owns a tile of
+// TC = 4096/L1 adjacent columns of one frame (64 KB of double2 whatever L1 is):
+//   1. all threads load the tile row by row, columns fastest: runs of TC samples / window values per row, ingest and window
+//      fused, products into shared memory;
+//   2. each team transforms its columns out of / back into the tile (in place: a thread reads rows tid + NT*m of its column and
+//      writes bins tid + NT*m of the same column), the exchange buffer of fft_tail beside it;
+//      bins leave multiplied by W_M^(n2*k), k = tid + NT*m: W_M^(n2*tid) times successive powers of W_M^(n2*NT), two table
+//      reads per thread and column (a per-element gather in step 3 cost a third of the kernel's stall samples);
+//   3. all threads write the tile to Z row by row, runs of TC elements.
+// The tile is swizzled (column c of row e sits in slot c ^ f(e)) so that both the row-wise and the column-wise accesses are free
+// of bank conflicts with 16-byte elements.
+template <int LOG2L> struct ColsTileCfg {
+    using C = SmemCfg<double, LOG2L>;
+    static constexpr int L = 1 << LOG2L;
+    static constexpr int LOG2TC = 12 - LOG2L, TC = 1 << LOG2TC;
+    static constexpr int ROUNDS = TC / C::TEAMS;
+    static constexpr int SW_SHIFT = TC >= 8 ? 0 : (TC == 4 ? 1 : 2);
+    static constexpr int SW_MASK = (TC >= 8 ? 8 : TC) - 1;
+    static constexpr int TILE_ELEMS = L * TC;
+    static constexpr int XCH_ELEMS = C::FPAD * C::TEAMS;                 // single exchange buffer (two barriers per exchange)
+    static constexpr int SMEM_BYTES = (TILE_ELEMS + XCH_ELEMS) * (int)sizeof(cd);
+    static_assert(TC >= C::TEAMS && TC % C::TEAMS == 0, "a tile is a whole number of rounds of the CTA's teams");
+    static_assert(TILE_ELEMS % C::CTA == 0, "the row-wise phases have no remainder");
+    static __device__ __forceinline__ int slot(int e, int c) { return e * TC + (c ^ ((e >> SW_SHIFT) & SW_MASK)); }
+};
+
+template <int LOG2L, int INFMT>
+__global__ void __launch_bounds__(SmemCfg<double, LOG2L>::CTA, 2)
+cols_tiled_kernel(const OpColsIn<INFMT, false> op, const cd* __restrict__ tw, int64_t nTiles) {
+    using C = SmemCfg<double, LOG2L>;
+    using TCfg = ColsTileCfg<LOG2L>;
+    constexpr int P = C::P, NT = C::NT, TEAMS = C::TEAMS, LOG2P = C::LOG2P, CTA = C::CTA;
+    constexpr int L0 = stage_l<LOG2L, LOG2P>(0);
+    constexpr int TC = TCfg::TC, LOG2TC = TCfg::LOG2TC;
+    constexpr int PER = TCfg::TILE_ELEMS / CTA, UNR = 16;        // 32 elements per thread and phase, two bursts of 16 (x2) loads
+    static_assert(PER % UNR == 0, "the row-wise phases are unrolled");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cd* tile = reinterpret_cast<cd*>(smem_raw);
+    const int team = (TEAMS > 1) ? (threadIdx.x / NT) : 0;
+    const int tid = (TEAMS > 1) ? (threadIdx.x % NT) : threadIdx.x;
+    cd* xbuf = tile + TCfg::TILE_ELEMS + team * C::FPAD;
+    auto sync = [] { __syncthreads(); };
+    const int l2 = op.g.l2;
+    const int tilesPerFrameLog = l2 - LOG2TC;
+    for (int64_t t = blockIdx.x; t < nTiles; t += gridDim.x) {
+        const int64_t fs = t >> tilesPerFrameLog;
+        const int64_t n2_0 = (t & (((int64_t)1 << tilesPerFrameLog) - 1)) << LOG2TC;
+        const int64_t s = fs / op.nFrames;
+        const int64_t base = s * op.scanStride + __ldg(&op.offs[fs - s * op.nFrames]);
+        // 1. rows of the tile, columns fastest
+#pragma unroll 1
+        for (int i0 = 0; i0 < PER; i0 += UNR) {
+            cd v[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int i = (i0 + u) * CTA + threadIdx.x;
+                const int64_t n = ((int64_t)(i >> LOG2TC) << l2) + n2_0 + (i & (TC - 1));
+                v[u] = Ingest<double, INFMT>::load(op.samples, base + n, __ldg(&op.win[n]), op.u8off, op.u8scale);
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int i = (i0 + u) * CTA + threadIdx.x;
+                tile[TCfg::slot(i >> LOG2TC, i & (TC - 1))] = v[u];
+            }
+        }
+        __syncthreads();
+        // 2. column transforms, in place in the tile
+#pragma unroll 1
+        for (int r = 0; r < TCfg::ROUNDS; ++r) {
+            const int c = r * TEAMS + team;
+            cd w = __ldg(&op.twM[(n2_0 + c) * tid]);
+            const cd wstep = __ldg(&op.twM[(n2_0 + c) * NT]);
+            cd b[P];
+#pragma unroll
+            for (int m = 0; m < P; ++m) b[m] = tile[TCfg::slot(tid + NT * m, c)];
+            butterflies<double, P, (1 << L0), false>(b, nullptr);
+            fft_tail<double, LOG2L, LOG2P, false, false, L0, 0, 0>(b, nullptr, tw, xbuf, xbuf, tid, sync);
+            // bin k = tid + NT*m of column n2 leaves multiplied by W_M^(n2*k) = W_M^(n2*tid) * (W_M^(n2*NT))^m: two table
+            // entries per thread and column (fetched before the transform) instead of one gather per element
+#pragma unroll
+            for (int m = 0; m < P; ++m) {
+                b[m] = cmul(b[m], w);
+                w = cmul(w, wstep);
+            }
+#pragma unroll
+            for (int m = 0; m < P; ++m) tile[TCfg::slot(tid + NT * m, c)] = b[m];
+        }
+        __syncthreads();
+        // 3. rows of the tile to Z
+        cd* zt = op.Z + fs * op.g.M + n2_0;
+#pragma unroll 8
+        for (int i = threadIdx.x; i < TCfg::TILE_ELEMS; i += CTA) {
+            const int k = i >> LOG2TC, c = i & (TC - 1);
+            zt[((int64_t)k << l2) + c] = tile[TCfg::slot(k, c)];
+        }
+        __syncthreads();            // the next tile's rows overwrite this one
+    }
+}
+
+template <int LOG2L, int INFMT>
+static int launch_cols_tiled(const OpColsIn<INFMT, false>& op, const cd* tw, int64_t nFrameSlabs, int smCount, cudaStream_t st) {
+    using TCfg = ColsTileCfg<LOG2L>;
+    auto k = cols_tiled_kernel<LOG2L, INFMT>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    const int64_t nTiles = nFrameSlabs << (op.g.l2 - TCfg::LOG2TC);
+    const int64_t cap = (int64_t)smCount * 2;
+    const int grid = (int)(nTiles < cap ? nTiles : cap);
+    k<<<grid, SmemCfg<double, LOG2L>::CTA, TCfg::SMEM_BYTES, st>>>(op, tw, nTiles);
+    return (int)cudaGetLastError();
+}
+
+constexpr int COLS_TILED_MIN_L = 8, COLS_TILED_MAX_L = 10;     // column lengths 256..1024: tiles of 16..4 columns
+
 // final row pass: a team owns row k1 of one scan and walks the scan's frames, |X| (scaled) cumulated in the registers
 // that own the bins (data_cumu, K:124-147); one store per bin and scan.  acc layout: [k1][k2] (four-step; the epilogue
 // un-permutes) or natural bin order (Bluestein, only bins < F exist).
@@ -171,8 +288,9 @@ struct RowsAccParams {
     BigGeom g; const cd* Z; double* acc; double scale; int cumuMode; int nFrames; int transposedAcc;
 };
 
-template <int LOG2L>
-__global__ void __launch_bounds__(SmemCfg<double, LOG2L>::CTA, 1)
+// OCC3: 128-thread CTAs three per SM (168 registers, no spills; two exchange buffers of 35 KB each) instead of two (204 registers)
+template <int LOG2L, bool OCC3>
+__global__ void __launch_bounds__(SmemCfg<double, LOG2L>::CTA, (OCC3 && SmemCfg<double, LOG2L>::CTA == 128 ? 3 : 1))
 team_fft_acc_kernel(const RowsAccParams p, const cd* __restrict__ tw, int64_t nBatch) {
     using C = SmemCfg<double, LOG2L>;
     constexpr int P = C::P, NT = C::NT, TEAMS = C::TEAMS, LOG2P = C::LOG2P;
@@ -221,15 +339,17 @@ team_fft_acc_kernel(const RowsAccParams p, const cd* __restrict__ tw, int64_t nB
     }
 }
 
-template <int LOG2L>
+template <int LOG2L, bool OCC3>
 static int launch_team_fft_acc(const RowsAccParams& p, const cd* tw, int64_t nBatch, int smCount, cudaStream_t st) {
     using C = SmemCfg<double, LOG2L>;
-    auto k = team_fft_acc_kernel<LOG2L>;
+    auto k = team_fft_acc_kernel<LOG2L, OCC3>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    int64_t need = (nBatch + C::TEAMS - 1) / C::TEAMS;
-    int64_t cap = (int64_t)smCount * 4;
-    int grid = (int)(need < cap ? need : cap);
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, C::CTA, C::SMEM_BYTES) != cudaSuccess || occ < 1) occ = 1;
+    const int64_t need = (nBatch + C::TEAMS - 1) / C::TEAMS;
+    const int64_t cap = (int64_t)smCount * occ * (OCC3 ? 1 : 2);     // whole waves of resident CTAs
+    const int grid = (int)(need < cap ? need : cap);
     k<<<grid, C::CTA, C::SMEM_BYTES, st>>>(p, tw, nBatch);
     return (int)cudaGetLastError();
 }
@@ -330,11 +450,12 @@ static int launch_bluestein_smem(const BlueSmallParams& p, int smCount, cudaStre
 
 // entry points of the separately compiled instantiation units
 int big_cols_in(int inFmt, int blue, int l1, const void* op, const cd* tw, int64_t nBatch, int smCount, cudaStream_t st);
+int big_cols_tiled(int inFmt, int l1, const void* op, const cd* tw, int64_t nFrameSlabs, int smCount, cudaStream_t st);
 int big_cols_plain(int l1, const OpColsPlain& op, const cd* tw, int64_t nBatch, int smCount, cudaStream_t st);
 int big_cols_mid(int l1, const OpColsMid& op, const cd* tw, int64_t nBatch, int smCount, cudaStream_t st);
 int big_rows_plain(int l2, const OpRowsPlain& op, const cd* tw, int64_t nBatch, int smCount, cudaStream_t st);
 int big_rows_mul(int l2, const OpRowsMul& op, const cd* tw, int64_t nBatch, int smCount, cudaStream_t st);
-int big_rows_acc(int l2, const RowsAccParams& p, const cd* tw, int64_t nBatch, int smCount, cudaStream_t st);
+int big_rows_acc(int l2, int occ3, const RowsAccParams& p, const cd* tw, int64_t nBatch, int smCount, cudaStream_t st);
 int big_plain(int l, const OpPlain& op, const cd* tw, int64_t nBatch, int smCount, cudaStream_t st);
 int big_blue_small(int inFmt, int logM, const BlueSmallParams& p, int smCount, cudaStream_t st);
 

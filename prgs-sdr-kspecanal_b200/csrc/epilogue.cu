@@ -18,9 +18,11 @@ __device__ __forceinline__ double d_inf() { return __longlong_as_double(0x7ff000
 
 // block = (FIN_X bins) x (FIN_Y slot groups): the per-team partials (888 of them after a batch of the headline shape) are reduced
 // by FIN_Y threads per bin in parallel over many small CTAs (the kernel is pure latency: 14 MB out of L2), then a tree in shared
-// memory and the y == 0 thread finishes the bin.
-constexpr int FIN_X = 8, FIN_Y = 64;
-template <typename T>
+// memory and the y == 0 thread finishes the bin.  Long frames (F > FIN_WIDE_F: the multi-pass engines, a handful of scans per batch)
+// have the parallelism in the bins instead: 128 bins x 4 slot groups per CTA, coalesced rows (the 8 x 64 shape spent 1.27 ms on
+// 262 144 CTAs of mostly idle threads at F = 2^21).
+constexpr int FIN_WIDE_F = 16384;
+template <typename T, int FIN_X, int FIN_Y>
 __global__ void __launch_bounds__(FIN_X * FIN_Y) stats_finish_kernel(const T* __restrict__ wsMax, const T* __restrict__ wsMin, int slots,
                                     const T* __restrict__ avgRows, int avgWin, int F, const double* __restrict__ carry,
                                     int firstIsSeed, double avgScale, double* __restrict__ out, int partialsLinear, T gain,
@@ -30,8 +32,10 @@ __global__ void __launch_bounds__(FIN_X * FIN_Y) stats_finish_kernel(const T* __
     const bool inb = j < F;
     double mx = -d_inf(), mn = d_inf();
     // the rows of the Avg recurrence (at most AVG_WINDOW = FIN_Y of them) are fetched by the y threads side by side: the
-    // sequential recurrence below then reads shared memory instead of paying one L2 round trip per row
-    for (int r = threadIdx.y; r < avgWin && inb; r += FIN_Y) shAvg[r][threadIdx.x] = (double)avgRows[(int64_t)r * F + j];
+    // sequential recurrence below then reads shared memory instead of paying one L2 round trip per row (8 x 64 shape only: the
+    // wide shape has a bin per lane and reads its rows coalesced, straight from global memory)
+    if (avgWin <= FIN_Y)
+        for (int r = threadIdx.y; r < avgWin && inb; r += FIN_Y) shAvg[r][threadIdx.x] = (double)avgRows[(int64_t)r * F + j];
     if (inb) {
 #pragma unroll 4
         for (int s = threadIdx.y; s < slots; s += FIN_Y) {
@@ -69,6 +73,7 @@ __global__ void __launch_bounds__(FIN_X * FIN_Y) stats_finish_kernel(const T* __
         if (avgWin <= FIN_Y) {
             for (; r < avgWin; ++r) a = (a + shAvg[r][threadIdx.x]) / 2;
         } else {
+#pragma unroll 8
             for (; r < avgWin; ++r) a = (a + (double)avgRows[(int64_t)r * F + j]) / 2;
         }
         a = (avgScale == 0.0) ? 0.0 : a * avgScale;
@@ -426,14 +431,22 @@ void launch_stats_finish(int prec, const void* wsMax, const void* wsMin, int slo
                          double gain, const PeerExchange* px, unsigned long long seq) {
     PeerExchange none;
     const PeerExchange& pe = px ? *px : none;
-    if (prec == KSPEC_PREC_F32)
-        stats_finish_kernel<float><<<nblk(F, FIN_X), dim3(FIN_X, FIN_Y), 0, st>>>((const float*)wsMax, (const float*)wsMin, slots,
-                                                                 (const float*)avgRows, avgWin, F, carry, firstIsSeed, avgScale, out,
-                                                                 partialsLinear, (float)gain, pe, seq);
-    else
-        stats_finish_kernel<double><<<nblk(F, FIN_X), dim3(FIN_X, FIN_Y), 0, st>>>((const double*)wsMax, (const double*)wsMin, slots,
-                                                                  (const double*)avgRows, avgWin, F, carry, firstIsSeed, avgScale, out,
-                                                                  partialsLinear, gain, pe, seq);
+    const bool wide = F > FIN_WIDE_F;
+    if (prec == KSPEC_PREC_F32) {
+        auto args = [&](auto k, int fx, int fy) {
+            k<<<nblk(F, fx), dim3(fx, fy), 0, st>>>((const float*)wsMax, (const float*)wsMin, slots, (const float*)avgRows, avgWin, F, carry,
+                                                    firstIsSeed, avgScale, out, partialsLinear, (float)gain, pe, seq);
+        };
+        if (wide) args(stats_finish_kernel<float, 128, 4>, 128, 4);
+        else args(stats_finish_kernel<float, 8, 64>, 8, 64);
+    } else {
+        auto args = [&](auto k, int fx, int fy) {
+            k<<<nblk(F, fx), dim3(fx, fy), 0, st>>>((const double*)wsMax, (const double*)wsMin, slots, (const double*)avgRows, avgWin, F, carry,
+                                                    firstIsSeed, avgScale, out, partialsLinear, gain, pe, seq);
+        };
+        if (wide) args(stats_finish_kernel<double, 128, 4>, 128, 4);
+        else args(stats_finish_kernel<double, 8, 64>, 8, 64);
+    }
 }
 
 void launch_peer_combine(const PeerExchange& px, unsigned long long seq, double* out, cudaStream_t st) {

@@ -223,6 +223,9 @@ def expected_big_path(F):
     (16384, 0.5, "hanning", "AVG", "c64"),          # float64 frames above 8192: four-step engine (2^14 = 128 x 128)
     (65536, 0.1, "ones", "MAX", "c128"),
     (1 << 18, 0.5, "kaiser", "AVG", "u8"),
+    (1 << 16, 0.25, "hamming", "MIN", "u8"),        # tiled column pass (bigfft_kernels.cuh): 256-point columns, tiles of 16
+    (1 << 19, 0.5, "hanning", "RAW", "c64"),        # 512-point columns, tiles of 8, 1024-point rows
+    (1 << 20, 0.1, "ones", "MAX", "c128"),          # 1024-point columns, tiles of 4
     (1200, 0.1, "hanning", "AVG", "c64"),           # Bluestein, M = 4096 (one fused kernel)
     (1001, 0.5, "hamming", "MIN", "c128"),          # odd length
     (8, 0.5, "ones", "AVG", "c64"),                 # below the fused kernel's minimum
@@ -492,6 +495,26 @@ def test_cfg4_full_size_two_to_the_21():
         got = plan.curscan(x)
     assert_db_close(got, ref, F64_TOL, "2^21")
     assert int(np.argmax(got)) == int(np.argmax(ref)) == F // 2 + int(round(300e3 * F / FS))
+
+
+@pytest.mark.parametrize("F,fmt", [(1 << 16, "c64"), (1 << 18, "c128"), (1 << 21, "u8")])
+def test_fourstep_tiled_column_pass_matches_the_elementwise_one(F, fmt, monkeypatch):
+    """cols_tiled_kernel (default for 256..1024-point columns) against team_fft_kernel<OpColsIn> (KSPEC_FOURSTEP_TILED=0, read
+    when the plan is created): same spectra to rounding (the tiled pass factors the twiddle into two table entries), three
+    scans so that the slabs of several frames and scans are in flight"""
+    S = O.full_size(F, FS)
+    win = O.window_table("kaiser", F)
+    x = synth.tones_noise(3 * S, seed=61, dtype=np.complex128, sigma=0.02)
+    raw = synth.to_u8_iq(x) if fmt == "u8" else (x.astype(np.complex64) if fmt == "c64" else x)
+    out = {}
+    for tiled in ("1", "0"):
+        monkeypatch.setenv("KSPEC_FOURSTEP_TILED", tiled)
+        with Plan(F, S, 0.25, win, "AVG", _ffi.in_format(raw)) as plan:
+            assert plan.path == "fourstep"
+            out[tiled] = plan.zerospan_batch(raw, 3, 19.1, O.adjust_xres(F, 512), "MAX", rows="db")
+    for k in ("rows", "hm_rows", "max", "min", "avg"):
+        assert np.max(np.abs(out["1"][k] - out["0"][k])) < 1e-9, k
+    assert np.array_equal(np.argmax(out["1"]["rows"], axis=1), np.argmax(out["0"]["rows"], axis=1))
 
 
 @pytest.mark.parametrize("engine", ["mixedradix", "bluestein"])

@@ -51,6 +51,7 @@ CONFIGS = [
     ("cfg5a scan 4096 ones r=0.1 f64", 4096, "ones", 0.1, "AVG", "f64", 1024, "c64"),
     ("reference default 16384 ones r=0.1 f32", 16384, "ones", 0.1, "AVG", "f32", 512, "c64"),
     ("cfg4 2^21 ones MAX r=0.1 (four-step) f64", 1 << 21, "ones", 0.1, "MAX", "f64", 4, "c64"),
+    ("cfg4 2^21 ones MAX r=0.1 (four-step, element-wise column pass) f64", 1 << 21, "ones", 0.1, "MAX", "f64", 4, "c64", {"KSPEC_FOURSTEP_TILED": "0"}),
     ("cfg4 2^21 ones MAX r=0.1 (mixed radix engine, forced) f64", 1 << 21, "ones", 0.1, "MAX", "f64", 4, "c64", {"KSPEC_FORCE_MIXED": "1"}),
     ("reference default 16384 ones r=0.1 (four-step) f64", 16384, "ones", 0.1, "AVG", "f64", 512, "c64"),
     ("reference default 16384 ones r=0.1 (mixed radix engine, forced) f64", 16384, "ones", 0.1, "AVG", "f64", 512, "c64", {"KSPEC_FORCE_MIXED": "1"}),
