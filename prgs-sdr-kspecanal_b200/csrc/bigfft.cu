@@ -56,7 +56,7 @@ struct BigFft {
     cd *dTwM = nullptr, *dTw1 = nullptr, *dTw2 = nullptr, *dChirp = nullptr, *dV = nullptr, *dZ = nullptr, *dP = nullptr;
     int64_t* dOffs = nullptr;
     int nOffs = 0;
-    bool rowsOcc3 = false;      // last row pass with three CTAs per SM (KSPEC_ROWS_OCC3=1)
+    bool rowsOcc3 = false;      // last row pass with three CTAs per SM
     bool tiledCols = false;     // four-step column pass through shared-memory tiles (cols_tiled_kernel)
     cd* dPw = nullptr;          // Bluestein: product slabs, one per frame of a chunk (dP is the single slab used at plan time)
     size_t zCap = 0;            // bytes allocated for dZ (and dPw)
@@ -114,8 +114,10 @@ BigFft* bigfft_create(int prec, int inFmt, int64_t F, int path, int64_t* convSiz
     *convSize = path == KSPEC_PATH_BLUESTEIN ? b->M : 0;
     {   // KSPEC_FOURSTEP_TILED=0 keeps the element-wise column pass (A/B measurements); read once, here
         const char* e = getenv("KSPEC_FOURSTEP_TILED");
+        // last row pass: three CTAs per SM for rows of 2048 points and more (2^21: 0.414 -> 0.349 ms per 22 frames), two below
+        // (2^14, 128-point rows: 13.0 vs 14.2 ms per batch with three); KSPEC_ROWS_OCC3=0/1 overrides
         const char* o = getenv("KSPEC_ROWS_OCC3");
-        b->rowsOcc3 = o && o[0] == '1';
+        b->rowsOcc3 = o ? o[0] == '1' : b->l2 >= 11;
         b->tiledCols = path == KSPEC_PATH_FOURSTEP && b->l1 >= COLS_TILED_MIN_L && b->l1 <= COLS_TILED_MAX_L && !(e && e[0] == '0');
     }
     const int64_t M = b->M;
